@@ -1,0 +1,80 @@
+"""CPU: the oracle restatement (oracle/fields.py) against golden vectors produced by the UNMODIFIED
+reference Python (tests/golden/make_scene_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.fields import SceneOracle, init_reference_like_state
+
+CASES = ['init_full', 'rand_c2f', 'rand_full']
+
+
+def load(golden_dir, tag):
+    z = np.load(os.path.join(golden_dir, f'scene_{tag}.npz'))
+    ml = float(z['max_level'])
+    sd = init_reference_like_state(200, seed=int(z['seed']), randomize=bool(z['randomize']), emb_scale=float(z['emb_scale']))
+    return z, sd, (None if ml < 0 else ml)
+
+
+def close(a, ref, rtol=2e-5, atol=2e-6):
+    a = a.detach().numpy() if torch.is_tensor(a) else a
+    np.testing.assert_allclose(a, ref, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize('tag', CASES)
+def test_forward_modes(golden_dir, tag):
+    z, sd, ml = load(golden_dir, tag)
+    sc = SceneOracle(sd, 1.01, 200, ml)
+    x, t, light = (torch.from_numpy(z[k]) for k in ('x', 't', 'light'))
+    with torch.no_grad():
+        for shading, ratio in (('albedo', 1.0), ('albedo_normal', 1.0), ('lambertian', 0.3), ('textureless', 0.55), ('normal', 1.0)):
+            sdf, sigma, color, normal, deform, raw = sc.forward(x, t, light, ratio=ratio, shading=shading)
+            close(sdf, z[f'{shading}.sdf']); close(sigma, z[f'{shading}.sigma'], rtol=1e-4)
+            shaded = shading in ('lambertian', 'textureless', 'normal')   # colour then depends on FD normals
+            close(color, z[f'{shading}.color'], rtol=1e-3 if shaded else 2e-5, atol=2e-4 if shaded else 2e-6)
+            close(deform, z[f'{shading}.deform'])
+            if normal is not None:
+                close(raw, z[f'{shading}.normal_raw'], rtol=1e-3, atol=2e-4)   # FD of fp32 sdf: cancellation
+                close(normal, z[f'{shading}.normal'], rtol=1e-3, atol=2e-4)
+        d = sc.density(x, t)
+        close(d['sdf'], z['density.sdf']); close(d['albedo'], z['density.albedo'])
+        d = sc.density(x, None)
+        close(d['sdf'], z['density_cano.sdf']); close(d['albedo'], z['density_cano.albedo'])
+        d = sc.density(x, t[:3], allow_shape=True, return_color=False)
+        close(d['sigma'], z['density_allow_shape.sigma'], rtol=1e-4)
+        n, raw = sc.normal(x, t=t)
+        close(raw, z['normal_warped.raw'], rtol=1e-3, atol=2e-4)
+        n, raw = sc.normal(x, topo=None)
+        close(raw, z['normal_cano.raw'], rtol=1e-3, atol=2e-4)
+        deform, topo = sc.warp(x, t)
+        close(deform, z['warp.deform']); close(topo, z['warp.topo'])
+        close(sc.code(t), z['code'], rtol=1e-6, atol=1e-6)
+        close(sc.background(light, t), z['background'])
+        o2, d2 = sc.pose_optimisation(x, light, torch.from_numpy(z['pose.ids']))
+        close(o2, z['pose.o'], rtol=1e-6); close(d2, z['pose.d'], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize('tag', CASES)
+def test_gradients(golden_dir, tag):
+    z, sd, ml = load(golden_dir, tag)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    sc = SceneOracle(sd, 1.01, 200, ml)
+    x, t, light = (torch.from_numpy(z[k]) for k in ('x', 't', 'light'))
+    M = x.shape[0]
+    xg = x.clone().requires_grad_(True)
+    sdf, sigma, color, normal, deform, raw = sc.forward(xg, t, light, ratio=1.0, shading='albedo_normal')
+    g = torch.Generator().manual_seed(77)
+    loss = (sdf * torch.randn(M, generator=g)).sum() + (sigma * torch.randn(M, generator=g)).sum() * 1e-2 \
+        + (color * torch.randn(M, 3, generator=g)).sum() + (normal * torch.randn(M, 3, generator=g)).sum() \
+        + (deform * torch.randn(M, 3, generator=g)).sum()
+    loss.backward()
+
+    def relerr(a, b):
+        return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+    assert relerr(xg.grad.numpy(), z['grad.x']) < 2e-3
+    for name in ('encoder.embeddings', 'encoder_c.embeddings', 'sdf_net.net.0.weight', 'sdf_net.net.2.bias',
+                 'color_net.net.1.weight_v', 'color_net.net.1.weight_g', 'deform_net.net.0.weight_v', 'deform_net.net.5.weight_g',
+                 'topo_net.net.3.weight_v', 'deform_code.volumes.0', 'deform_code.volumes.2', 'sdf2density.beta'):
+        assert relerr(sd[name].grad.numpy(), z['grad.' + name]) < 2e-3, name
