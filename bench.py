@@ -1,0 +1,252 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the MorpheuS render-and-loss hot path.
+
+Workload (BASELINE.json configs[1]): snoopy-shaped synthetic RGB-D, 4096 rays x 128 samples per step,
+real-view TRAINING step = pose correction -> fixed-S sampling -> fused scene query (deform + topology MLPs,
+hash grids, SDF + colour MLPs, 6-point FD normals: 'albedo_normal') -> Laplace sigma -> alpha compositing
+-> perturbed-normal query (6 more SDF queries/sample) -> losses -> fused backward -> [NCCL all-reduce of the
+flat gradient arena] -> fused Adam.  13 SDF queries per sample, the reference's real-view mix.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+Under torchrun (N > 1) the global ray batch is split over ranks (strong scaling), one all-reduce per step.
+Prints ONE JSON line (rank 0).  `value` = rays/s with inputs resident in HBM; `e2e` = same step with the
+batch copied from pinned host memory and the loss read back every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RAYS, N_SAMPLES, NUM_FRAMES, MAX_LEVEL = 4096, 128, 200, 1.0
+CONFIG = {'model': {'bg_radius': 1.4, 'activation': 'exp'}, 'render': {'step_size': 0.01}}
+# algorithmic MACs per sample (SURVEY.md 8d / BASELINE.md section 2)
+MAC_DEFORM, MAC_TOPO, MAC_COLOR, MAC_SDF = 77056, 76928, 8384, 10880
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('bf16_tflops_sustained', 1400.0), d.get('hbm_gbs', 6650.0), 'measured (MEASURED_PEAKS.json, sustained)'
+    return 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={q}', '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace('.', '').isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith('active')})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons, 'samples': len(sm)}
+
+
+def make_state():
+    """seeded reference-style initial state (geometric-init SDF ~ sphere of radius 0.4, weight_norm g=|v|, U(-1e-4,1e-4) tables)"""
+    torch.manual_seed(2024)   # morpheus.py:45 seed_everything(2024)
+    from morpheus_b200.model import scene_representation
+    m = scene_representation(CONFIG, 1.01, num_frames=NUM_FRAMES, deform_dim=16, use_app=False, use_t=False, amb_dim=2,
+                             color_grid=True, use_joint=True, encode_topo=False)
+    m.max_level = MAX_LEVEL
+    return m
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the same step on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step_seconds(state_dict, n_rays, repeats):
+    """the ONLY place bench.py executes oracle/: the CPU checker timed as the CPU baseline."""
+    from oracle import train_step as ots
+    from morpheus_b200.rays import synthetic_real_view_batch
+    torch.set_num_threads(os.cpu_count())
+    params = ots.make_params({k: v.detach().cpu().clone() for k, v in state_dict.items()})
+    opt = torch.optim.Adam([v for v in params.values() if v.requires_grad], lr=5e-4, betas=(0.9, 0.99), eps=1e-15)
+    times = []
+    for r in range(repeats):
+        batch = synthetic_real_view_batch(n_rays, seed=100 + r)
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss, _ = ots.step_loss(params, batch, N_SAMPLES, MAX_LEVEL)
+        loss.backward()
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    m = make_state()
+    n_rays = 64          # bounded sample of the 4096-ray step: 64 rays x 128 samples x 13 SDF queries
+    times = cpu_step_seconds(m.state_dict(), n_rays, args.warmup + args.steps)[args.warmup:]
+    sec = sum(times) / len(times)
+    val = n_rays / sec
+    cores = os.cpu_count()
+    line = {'impl': 'reference', 'metric': 'rays_per_sec_train_step', 'value': val, 'unit': 'rays/s', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': sec * 1e3 * (N_RAYS / n_rays), 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args.gpus),
+            'cpu_baseline': {'value': val, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'{n_rays} rays x {N_SAMPLES} samples per step (1/{N_RAYS // n_rays} of the workload), fwd+bwd+Adam, torch CPU oracle port; '
+                                       'the reference hash-grid kernel is CUDA-only so its own CPU path does not exist'},
+            'e2e': {'value': val, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {'workload': f'snoopy-shape synthetic RGB-D, {N_RAYS} rays x {N_SAMPLES} samples, real-view train step (albedo_normal + perturbed-normal reg: '
+                        '13 SDF queries/sample), fwd+bwd+allreduce+Adam', 'rays': N_RAYS, 'samples_per_ray': N_SAMPLES, 'frames': NUM_FRAMES,
+            'parallelism': f'ray-sharded dp{n_gpus}', 'l2_flush': '256 MiB write between timed steps (inside the timed region)'}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--cpu-baseline-steps', type=int, default=2)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3 if args.impl == 'ours' else 1)
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    import torch.distributed as dist
+    from morpheus_b200 import train as mtrain
+    from morpheus_b200.nerfacc_compat import OccGridEstimator
+    from morpheus_b200.rays import synthetic_real_view_batch
+    from morpheus_b200.render import Renderer
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    model = make_state().to(dev).train()
+    state_for_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()} if rank == 0 else None
+    tr = dict(mtrain.DEFAULT_TRAIN_CFG)
+    cfg = dict(CONFIG, train=tr)
+    R = Renderer(model, OccGridEstimator(torch.tensor([-1.01] * 3 + [1.01] * 3), 128).to(dev), cfg, NUM_FRAMES, uniform_samples=N_SAMPLES)
+    opt = mtrain.FlatAdam(model, tr['lr'])
+    n_local = N_RAYS // world
+    total_steps = args.warmup + args.steps
+    # pinned host batches (one per step, distinct pixels/frames); each rank keeps its contiguous shard
+    host = []
+    for s in range(total_steps):
+        b = synthetic_real_view_batch(N_RAYS, seed=1000 + s, frame=(37 * s) % NUM_FRAMES)
+        host.append({k: v[rank * n_local:(rank + 1) * n_local].contiguous().pin_memory() for k, v in b.items()})
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def to_dev(b):
+        return {k: v.to(dev, non_blocking=True) for k, v in b.items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(e2e, profile):
+        resident = [to_dev(b) for b in host] if not e2e else None
+        torch.cuda.synchronize()
+        loss_host = torch.zeros(1).pin_memory()
+        for s in range(args.warmup):
+            b = to_dev(host[s]) if e2e else resident[s]
+            loss = mtrain.train_step(R, opt, b, tr, world)
+        barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        prof.enabled = profile
+        prof.reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(args.warmup, total_steps):
+            flush.fill_(s & 0xFF)
+            b = to_dev(host[s]) if e2e else resident[s]
+            loss = mtrain.train_step(R, opt, b, tr, world)
+            if e2e:
+                loss_host.copy_(loss.reshape(1), non_blocking=True)
+                torch.cuda.current_stream().synchronize()   # the user reads the loss every step (morpheus.py:1426 loss.item())
+        e1.record()
+        barrier()
+        prof.enabled = False
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), clocks, float(loss)
+
+    from morpheus_b200 import model as mmodel
+    prof = mmodel.PROFILE
+    ms_total, clocks, last_loss = run(e2e=False, profile=True)
+    kern = prof.summary()
+    ms_e2e, _, _ = run(e2e=True, profile=False)
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        value = N_RAYS / (ms_step * 1e-3)
+        e2e_val = N_RAYS / (ms_e2e / args.steps * 1e-3)
+        tf_peak, hbm_peak, which = peaks()
+        # dominant kernel: the fused backward of the main query (WARP|MAIN|COLOR|FD: 1 + 6 SDF queries), dgrad + wgrad = 2x forward MACs
+        M_local = n_local * N_SAMPLES
+        macs_fwd_main = MAC_DEFORM + MAC_TOPO + MAC_COLOR + 7 * MAC_SDF
+        flops_bwd_main = 2 * 2 * macs_fwd_main * M_local
+        k = kern.get('field_bwd_main', None)
+        roof = None
+        if k:
+            ach = flops_bwd_main / (k['avg_ms'] * 1e-3) / 1e12
+            roof = {'kernel': 'field_bwd_kernel (main query)', 'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak,
+                    'traffic': None, 'peak_source': which, 'avg_launch_ms': k['avg_ms'], 'launches_timed': k['n'],
+                    'algorithmic_flops_per_launch': flops_bwd_main,
+                    'note': 'fp32 SIMT engine (round 1): its own ceiling is the fp32 FMA pipe (~72 TFLOP/s), see DESIGN.md'}
+        launches = sum(v['n'] for v in kern.values()) // args.steps if kern else None
+        times = cpu_step_seconds(state_for_cpu, 64, 1 + args.cpu_baseline_steps)[1:]
+        cpu_val = 64 / (sum(times) / len(times))
+        line = {'metric': 'rays_per_sec_train_step', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': workload_config(world), 'clocks': clocks,
+                'e2e': {'value': e2e_val, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
+                'gpu_launches': launches, 'kernels': kern, 'final_loss': last_loss,
+                'roofline': roof,
+                'cpu_baseline': {'value': cpu_val, 'unit': 'rays/s', 'cores': os.cpu_count(), 'kind': 'port',
+                                 'sample': f'64 rays x {N_SAMPLES} samples (1/64 of the step), fwd+bwd+Adam, {args.cpu_baseline_steps} timed steps after 1 warm-up, oracle port on torch CPU'}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,179 @@
+/*
+ * morpheus_b200 -- C ABI of the B200-native MorpheuS render-and-loss hot path.
+ *
+ * Every entry point: extern "C", plain pointers + sizes, returns 0 on success or a negative
+ * MB_E* code (text via mb_last_error()).  All pointers are DEVICE pointers owned by the caller
+ * unless stated otherwise; nothing is allocated or freed inside (same ownership rule as the
+ * reference extension: external/encoders/gridencoder/grid.py:50,56,84,87).  `stream` is a
+ * cudaStream_t passed as void* (the reference launches on the legacy default stream,
+ * gridencoder.cu:386; we take the caller's stream so CUDA graphs / NCCL overlap work).
+ *
+ * Reference interfaces replaced (file:line relative to /root/reference):
+ *   mb_grid_encode_forward/backward  <- external/encoders/gridencoder/src/gridencoder.h:12-13
+ *                                       (bindings.cpp:6-7, called from grid.py:61,91)
+ *   mb_sample_rays_*                 <- nerfacc OccGridEstimator.sampling        (morpheus.py:629-638)
+ *   mb_composite_*                   <- nerfacc render_weight_from_density +
+ *                                       accumulate_along_rays                   (morpheus.py:675-685)
+ *   mb_field_forward/backward        <- scene_representation.forward/density/normal/warp
+ *                                       (models/model.py:273-307,367-398,412-437,439-533)
+ *   mb_occ_update                    <- nerfacc OccGridEstimator.update_every_n_steps (morpheus.py:905-913)
+ *   mb_adam_step                     <- torch.optim.Adam over get_params_all()   (morpheus.py:154-155)
+ *   mb_sds_grad                      <- Zero123.train_step scalar math           (models/guidance/zero123_utils.py:177-212)
+ */
+#ifndef MORPHEUS_B200_H
+#define MORPHEUS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_OK 0
+#define MB_EINVAL (-1)      /* bad argument (null pointer, unsupported D/C/dtype ...) */
+#define MB_ECUDA (-2)       /* CUDA runtime error at launch */
+#define MB_EUNSUPPORTED (-3)
+
+#define MB_DTYPE_F32 0
+
+typedef void* mb_stream_t;
+
+int mb_version(void);
+const char* mb_last_error(void);
+/* number of SMs of the current device (grid sizing is a multiple of this) */
+int mb_sm_count(void);
+
+/* ---- (1) grid encoder: argument order follows gridencoder.h:12-13 exactly ------------------- */
+/* inputs [B,D] f32 in [0,1]; embeddings [sO,C]; offsets [L+1] i32; outputs [L,B,C] (caller
+ * zero-fills levels >= max_level, grid.py:53); dy_dx [B, L*D*C] or NULL.
+ * Supported: D in {2,3}, C in {1,2,4,8}, dtype f32, gridtype 0 hash / 1 tiled,
+ * interp 0 linear / 1 smoothstep.  Anything else -> MB_EUNSUPPORTED (the reference throws
+ * std::runtime_error, gridencoder.cu:392,409). */
+int mb_grid_encode_forward(const float* inputs, const void* embeddings, const int32_t* offsets, void* outputs,
+                           uint32_t B, uint32_t D, uint32_t C, uint32_t L, uint32_t max_level, float S, uint32_t H,
+                           void* dy_dx, uint32_t gridtype, int align_corners, uint32_t interp, int dtype,
+                           mb_stream_t stream);
+/* grad [L,B,C]; grad_embeddings [sO,C] pre-zeroed by caller (grid.py:84), accumulated with
+ * red.global.add; grad_inputs [B,D] or NULL (written, not accumulated). */
+int mb_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings, const int32_t* offsets,
+                            void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, uint32_t max_level,
+                            float S, uint32_t H, const void* dy_dx, void* grad_inputs, uint32_t gridtype,
+                            int align_corners, uint32_t interp, int dtype, mb_stream_t stream);
+
+/* ---- (2) ray sampling through a binary occupancy grid ---------------------------------------- */
+/* Two passes (count, then write after an exclusive scan by the caller).  rays_o/rays_d [N,3];
+ * binaries [res^3] uint8 (x-major: idx = (ix*res+iy)*res+iz, nerfacc layout); aabb[6] host floats;
+ * jitter [N] in [0,1) or NULL.  counts [N] i32. */
+int mb_sample_rays_count(const float* rays_o, const float* rays_d, uint32_t N, const uint8_t* binaries, uint32_t res,
+                         const float* aabb_host6, float step, float near_plane, float far_plane, const float* jitter,
+                         int32_t* counts, mb_stream_t stream);
+/* offsets [N] i32 exclusive scan of counts; writes ray_indices [M] i64, t_starts [M], t_ends [M]. */
+int mb_sample_rays_write(const float* rays_o, const float* rays_d, uint32_t N, const uint8_t* binaries, uint32_t res,
+                         const float* aabb_host6, float step, float near_plane, float far_plane, const float* jitter,
+                         const int32_t* offsets, int64_t* ray_indices, float* t_starts, float* t_ends,
+                         mb_stream_t stream);
+/* fixed-S lattice over the AABB chord (BASELINE cfg-1/2/4 synthetic sampler): writes [N*S] triples. */
+int mb_sample_rays_uniform(const float* rays_o, const float* rays_d, uint32_t N, uint32_t S, const float* aabb_host6,
+                           const float* jitter, int64_t* ray_indices, float* t_starts, float* t_ends,
+                           mb_stream_t stream);
+
+/* ---- (3) compositing -------------------------------------------------------------------------- */
+/* Packed samples sorted by ray; seg [N+1] i32 = first sample of each ray (seg[N] = M).
+ * sigmas/t_starts/t_ends [M]; rgbs [M,3] or NULL.  Outputs (any may be NULL): weights/trans/alphas [M],
+ * opacity [N], depth [N] (sum w*(t0+t1)/2), rgb [N,3]. */
+int mb_composite_forward(const int32_t* seg, uint32_t N, uint32_t M, const float* sigmas, const float* t_starts,
+                         const float* t_ends, const float* rgbs, float* weights, float* trans, float* alphas,
+                         float* opacity, float* depth, float* rgb, mb_stream_t stream);
+/* Upstream grads (any may be NULL = zero): g_weights [M], g_opacity [N], g_depth [N], g_rgb [N,3].
+ * Writes g_sigmas [M] and g_rgbs [M,3] (if rgbs != NULL). */
+int mb_composite_backward(const int32_t* seg, uint32_t N, uint32_t M, const float* sigmas, const float* t_starts,
+                          const float* t_ends, const float* rgbs, const float* g_weights, const float* g_opacity,
+                          const float* g_depth, const float* g_rgb, float* g_sigmas, float* g_rgbs,
+                          mb_stream_t stream);
+
+/* ---- (4) fused scene-field query ---------------------------------------------------------------- */
+#define MB_F_WARP 1u          /* deform/topo MLPs from (x, t)                       model.py:412-437 */
+#define MB_F_MAIN 2u          /* sdf (+sigma) at x+deform                           model.py:273-293 */
+#define MB_F_COLOR 4u         /* colour grid + colour MLP (needs MAIN)              model.py:295-302 */
+#define MB_F_FD 8u            /* 6-point finite-difference normal                   model.py:367-398 */
+#define MB_F_FD_WARPED 16u    /* ... evaluated at x+deform instead of x             model.py:391-395 */
+#define MB_F_TOPO_IN 32u      /* take topo from topo_in instead of zeros / warp */
+#define MB_SHADE_ALBEDO 0
+#define MB_SHADE_LAMBERTIAN 1   /* albedo*(ratio+(1-ratio)*max(n.l,0)); 'albedo_normal' is ratio=1 */
+#define MB_SHADE_TEXTURELESS 2
+#define MB_SHADE_NORMAL 3
+
+/* Offsets (in floats) into the packed parameter arena, produced by morpheus_b200.packing. Each
+ * dense layer stores Wt[K_pad][N_pad] (k-major, forward operand), W[N_pad][K_pad] (n-major,
+ * dgrad operand) and bias[N_pad]; the gradient arena uses the same offsets (dW is accumulated
+ * into the Wt slot only). */
+typedef struct mb_layer_desc {
+    uint32_t wt_off, w_off, b_off;
+    uint32_t K, N, K_pad, N_pad;
+} mb_layer_desc;
+
+typedef struct mb_field_params {
+    const float* arena;             /* packed effective weights (weight_norm already applied) */
+    mb_layer_desc deform[6], topo[6], sdf[3], color[3];
+    const float* emb_sdf;           /* [sO,2] */
+    const float* emb_col;           /* [sO,2] */
+    const int32_t* offsets;         /* [17] */
+    const float* code[3];           /* deform_code.volumes.i as [16, S_i] */
+    uint32_t code_len[3];
+    const float* beta;              /* device scalar: abs(beta_param)+1e-4 (device-side so no host sync is needed) */
+    float bound;                    /* 1.01 */
+    float two_bound;                /* (float)(2*bound) evaluated in double first, as Python does (grid.py:157) */
+    float S; uint32_t H;            /* log2(per_level_scale), base resolution */
+    uint32_t n_levels;              /* ceil(max_level*16) clamped [1,16] */
+    uint32_t n_freq;                /* int(max_level*6) */
+} mb_field_params;
+
+typedef struct mb_field_io {
+    uint32_t M;
+    uint32_t flags; int shading; float ratio;
+    const float* x;                 /* [M,3] */
+    const float* t;                 /* [M]  (needed with WARP) */
+    const float* light;             /* [M,3] or NULL */
+    const float* topo_in;           /* [M,2] or NULL */
+    /* outputs, each may be NULL */
+    float* sdf; float* sigma; float* color; float* normal; float* normal_raw; float* deform; float* topo;
+} mb_field_io;
+
+int mb_field_forward(const mb_field_params* p, const mb_field_io* io, mb_stream_t stream);
+
+typedef struct mb_field_grads {
+    /* upstream (NULL = zero) */
+    const float* g_sdf; const float* g_sigma; const float* g_color; const float* g_normal; const float* g_normal_raw; const float* g_deform; const float* g_topo;
+    /* saved from forward: deform [M,3], topo [M,2] (required with WARP); normal_raw [M,3] (required with FD) */
+    const float* deform; const float* topo; const float* normal_raw;
+    /* accumulated (caller zero-fills): */
+    float* g_arena; float* g_emb_sdf; float* g_emb_col; float* g_code[3]; float* g_beta;
+    /* written: */
+    float* g_x;                     /* [M,3] or NULL */
+    float* g_topo_in;               /* [M,2] or NULL */
+} mb_field_grads;
+
+int mb_field_backward(const mb_field_params* p, const mb_field_io* io, const mb_field_grads* g, mb_stream_t stream);
+
+/* ---- (5) occupancy refresh: occs = max(decay*occs, sigma*step) on selected cells ---------------- */
+int mb_occ_update(float* occs, const int64_t* cell_idx, const float* sigma, uint32_t n, float decay, float step,
+                  mb_stream_t stream);
+int mb_occ_binarize(const float* occs, uint32_t n, float thre, uint8_t* binaries, mb_stream_t stream);
+
+/* ---- (6) fused Adam over a flat arena ------------------------------------------------------------ */
+/* p,g,m,v [n]; lr_scale [n_groups] device floats indexed by group_id [n] u8 (per-parameter-group lr,
+ * models/model.py:313-324); bias-corrected torch.optim.Adam semantics, no weight decay. */
+int mb_adam_step(float* p, const float* g, float* m, float* v, const uint8_t* group_id, const float* group_lr,
+                 uint64_t n, float beta1, float beta2, float eps, int step, mb_stream_t stream);
+
+/* ---- (7) SDS scalar chain: grad = grad_scale*(1-abar_t)*(eps_u + s*(eps_c-eps_u) - eps), nan_to_num --- */
+int mb_sds_grad(const float* eps_uncond, const float* eps_cond, const float* noise, float guidance_scale,
+                float w_t_times_grad_scale, float* grad, uint32_t n, mb_stream_t stream);
+/* latents_noisy = sqrt(abar)*z + sqrt(1-abar)*eps */
+int mb_add_noise(const float* z, const float* eps, float sqrt_abar, float sqrt_one_minus_abar, float* out, uint32_t n,
+                 mb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MORPHEUS_B200_H */

@@ -1,0 +1,448 @@
+"""B200-native `scene_representation` -- host-side mirror of /root/reference/models/model.py:31.
+
+Same constructor, attribute, method and state_dict surface as the reference class (SURVEY.md
+8b: `forward/__call__`, `density`, `normal`, `warp`, `get_topo`, `get_sigma_albedo`,
+`get_deform_code`, `background`, `pose_optimisation`, `get_RT`, `get_params_all`, `.max_level`,
+`.sdf2density.get_beta()`, `.pose_array`; keys `encoder.embeddings`, `sdf_net.net.N.weight`,
+`deform_net.net.N.weight_g/_v`, `deform_code.volumes.i`, `sdf2density.beta`, `pose_array.data`),
+but every per-sample query runs in ONE fused CUDA launch (csrc/field_fwd.cu) and its backward in
+one more (csrc/field_bwd.cu) instead of ~300 eager kernels with [M, .] intermediates in HBM.
+The sub-modules below only own parameters; their torch `forward`s exist for the tiny side paths
+(background colour, code regulariser) that the reference also runs outside the hot loop.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, packing
+from ._lib import F_COLOR, F_FD, F_FD_WARPED, F_MAIN, F_TOPO_IN, F_WARP, SHADE, check, ptr, stream
+from .gridencoder import GridEncoder
+
+PROFILE = _lib.PROFILE
+
+
+def safe_normalize(x, eps=1e-20):
+    """utils.py:70-71"""
+    return x / torch.sqrt(torch.clamp(torch.sum(x * x, -1, keepdim=True), min=eps))
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers (names/shapes of SURVEY.md Appendix B)
+# ------------------------------------------------------------------------------------------------
+class MLP(nn.Module):
+    """models/decoders.py:9-64: Linear stack, ReLU between, optional geometric init, weight_norm default."""
+
+    def __init__(self, dim_in, dim_out, dim_hidden, num_layers, bias=True, geo_init=False, inside_outside=False,
+                 geo_bias=0.5, weight_norm=True, bias_init=None):
+        super().__init__()
+        self.dim_in, self.dim_out, self.dim_hidden, self.num_layers = dim_in, dim_out, dim_hidden, num_layers
+        self.uses_weight_norm = weight_norm
+        net = []
+        for l in range(num_layers):
+            d_in = dim_in if l == 0 else dim_hidden
+            d_out = dim_out if l == num_layers - 1 else dim_hidden
+            lin = nn.Linear(d_in, d_out, bias=bias)
+            if geo_init:
+                with torch.no_grad():
+                    if l == num_layers - 1:
+                        sign = -1.0 if inside_outside else 1.0
+                        lin.weight.normal_(mean=sign * np.sqrt(np.pi) / np.sqrt(d_in), std=0.0001)
+                        lin.bias.fill_(-sign * geo_bias)
+                    elif l == 0:
+                        lin.bias.zero_()
+                        lin.weight[:, 3:].zero_()
+                        lin.weight[:, :3].normal_(0.0, np.sqrt(2) / np.sqrt(d_out))
+                    else:
+                        lin.bias.zero_()
+                        lin.weight.normal_(0.0, np.sqrt(2) / np.sqrt(d_out))
+            if bias_init is not None and l == num_layers - 1:
+                nn.init.constant_(lin.bias, -bias_init)
+            if weight_norm:
+                lin = nn.utils.weight_norm(lin)
+            net.append(lin)
+        self.net = nn.ModuleList(net)
+
+    def effective(self):
+        """[(W [out,in], b [out])] with weight_norm applied: W = g * v / ||v||_row."""
+        out = []
+        for lin in self.net:
+            if self.uses_weight_norm:
+                v, g = lin.weight_v, lin.weight_g
+                W = v * (g / v.norm(dim=1, keepdim=True))
+            else:
+                W = lin.weight
+            out.append((W, lin.bias))
+        return out
+
+    def forward(self, x):
+        for l, (W, b) in enumerate(self.effective()):
+            x = F.linear(x, W, b)
+            if l != self.num_layers - 1:
+                x = F.relu(x)
+        return x
+
+
+class MultiCode(nn.Module):
+    """models/deform_code.py:5-42: three learnable 1-D feature lines sampled at t."""
+
+    def __init__(self, sizes, c):
+        super().__init__()
+        self.volumes = nn.ParameterList([nn.Parameter(torch.randn((1, c, size, 1))) for size in sizes])
+
+    def sample(self, t):
+        t = t.clamp(0, 1).reshape(-1)
+        feats = []
+        for v in self.volumes:
+            line = v[0, :, :, 0]
+            S = line.shape[1]
+            pos = ((t * 2 - 1) + 1) / 2 * (S - 1)
+            i0 = torch.floor(pos).long().clamp(0, S - 1)
+            i1 = (i0 + 1).clamp(0, S - 1)
+            w1 = pos - i0.to(pos.dtype)
+            valid = ((i0 + 1) <= S - 1).to(pos.dtype)
+            feats.append((line[:, i0] * (1 - w1) + line[:, i1] * w1 * valid).t())
+        return torch.cat(feats, dim=-1)
+
+    def get_code(self, level=-1):
+        return self.volumes[level].squeeze().permute(1, 0)
+
+
+class LaplaceDensity(nn.Module):
+    """models/density.py:17-31."""
+
+    def __init__(self, params_init=None, beta_min=0.0001):
+        super().__init__()
+        for k, v in (params_init or {}).items():
+            setattr(self, k, nn.Parameter(torch.tensor(v)))
+        self.beta_min = beta_min
+
+    def get_beta(self):
+        return self.beta.abs() + self.beta_min
+
+    def density_func(self, sdf, beta=None):
+        if beta is None:
+            beta = self.get_beta()
+        return (1 / beta) * (0.5 + 0.5 * sdf.sign() * torch.expm1(-sdf.abs() / beta))
+
+    def forward(self, sdf, beta=None):
+        return self.density_func(sdf, beta=beta)
+
+
+class PoseArray(nn.Module):
+    """models/pose.py:4-64."""
+
+    def __init__(self, num_frames):
+        super().__init__()
+        self.num_frames = num_frames
+        self.num_params = 6
+        self.data = nn.Parameter(torch.zeros([num_frames, 6], dtype=torch.float32))
+
+    def forward(self, ids):
+        return self.data[ids]
+
+    def get_translations(self, ids):
+        tr = self.data[:, 3:6][ids]
+        return tr[None, ...] if tr.dim() == 1 else tr
+
+    def get_rotations(self, ids):
+        return self.data[:, 0:3][ids]
+
+    def get_rotation_matrices(self, ids):
+        r = self.get_rotations(ids)
+        if r.dim() == 1:
+            r = r[None, ...]
+        ca, cb, cg = torch.cos(r[:, 0]), torch.cos(r[:, 1]), torch.cos(r[:, 2])
+        sa, sb, sg = torch.sin(r[:, 0]), torch.sin(r[:, 1]), torch.sin(r[:, 2])
+        c1 = torch.stack([ca * cb, sa * cb, -sb], -1)
+        c2 = torch.stack([ca * sb * sg - sa * cg, sa * sb * sg + ca * cg, cb * sg], -1)
+        c3 = torch.stack([ca * sb * cg + sa * sg, sa * sb * cg - ca * sg, cb * cg], -1)
+        return torch.stack([c1, c2, c3], -1)
+
+
+class FreqEncoder_torch(nn.Module):
+    """models/encodings.py:10-57 (used only off the hot path: background colour)."""
+
+    def __init__(self, input_dim, max_freq_log2, N_freqs, **_):
+        super().__init__()
+        self.input_dim, self.N_freqs = input_dim, N_freqs
+        self.output_dim = input_dim + input_dim * N_freqs * 2
+        self.freq_bands = [float(2 ** k) for k in np.linspace(0, max_freq_log2, N_freqs)]
+
+    def forward(self, x, max_level=None, **kwargs):
+        n_on = self.N_freqs if max_level is None else int(max_level * self.N_freqs)
+        out = [x]
+        for k in range(n_on):
+            out += [torch.sin(x * self.freq_bands[k]), torch.cos(x * self.freq_bands[k])]
+        if self.N_freqs - n_on > 0:
+            out.append(torch.zeros(*x.shape[:-1], (self.N_freqs - n_on) * 2 * x.shape[-1], device=x.device, dtype=x.dtype))
+        return torch.cat(out, dim=-1)
+
+
+def get_encoder(encoding, input_dim=3, multires=6, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19,
+                desired_resolution=2048, align_corners=False, interpolation='linear', **kwargs):
+    """models/encodings.py:59-90 restricted to the encoders MorpheuS instantiates (models/model.py:101-167)."""
+    if encoding == 'frequency_torch':
+        enc = FreqEncoder_torch(input_dim=input_dim, max_freq_log2=multires - 1, N_freqs=multires)
+    elif encoding in ('hashgrid', 'tiledgrid'):
+        enc = GridEncoder(input_dim=input_dim, num_levels=num_levels, level_dim=level_dim, base_resolution=base_resolution,
+                          log2_hashmap_size=log2_hashmap_size, desired_resolution=desired_resolution,
+                          gridtype='hash' if encoding == 'hashgrid' else 'tiled', align_corners=align_corners, interpolation=interpolation)
+    else:
+        raise NotImplementedError(f'encoding {encoding!r}: MorpheuS only builds frequency_torch / hashgrid (SURVEY.md 2, rows 7 and 16)')
+    return enc, enc.output_dim
+
+
+# ------------------------------------------------------------------------------------------------
+# the fused query as an autograd op
+# ------------------------------------------------------------------------------------------------
+class _FieldQuery(torch.autograd.Function):
+    """One fused launch forward (mb_field_forward), one fused launch backward (mb_field_backward).
+    Tensor inputs: x, t, light, topo_in, arena, emb_sdf, emb_col, code0..2, beta.
+    Outputs: sdf, sigma, color, normal, normal_raw, deform, topo (None where not requested)."""
+
+    @staticmethod
+    def forward(ctx, cfg, x, t, light, topo_in, arena, emb_sdf, emb_col, code0, code1, code2, beta):
+        flags, shading, ratio, n_levels, n_freq, offsets, bound, S, H = cfg
+        M = x.shape[0]
+        dev = x.device
+        x = x.contiguous().float()
+        t = t.contiguous().float().reshape(-1) if t is not None else None
+        light = light.contiguous().float() if light is not None else None
+        topo_in = topo_in.contiguous().float() if topo_in is not None else None
+        codes = [c.detach().reshape(c.shape[1], c.shape[2]).contiguous() for c in (code0, code1, code2)]
+        P = packing.fill_descs(_lib.FieldParams())
+        P.arena = ptr(arena.detach())
+        P.emb_sdf, P.emb_col, P.offsets = ptr(emb_sdf.detach()), ptr(emb_col.detach()), ptr(offsets)
+        for i in range(3):
+            P.code[i] = codes[i].data_ptr()
+            P.code_len[i] = codes[i].shape[1]
+        beta_d = beta.detach().reshape(1).contiguous().float()
+        P.beta = ptr(beta_d)
+        P.bound, P.two_bound, P.S, P.H = bound, float(2 * bound), S, H
+        P.n_levels, P.n_freq = n_levels, n_freq
+        io = _lib.FieldIO()
+        io.M, io.flags, io.shading, io.ratio = M, flags, shading, float(ratio)
+        io.x, io.t, io.light, io.topo_in = ptr(x), ptr(t), ptr(light), ptr(topo_in)
+
+        def out(n, cond):
+            return torch.empty((M, n) if n > 1 else (M,), device=dev, dtype=torch.float32) if cond else None
+        sdf, sigma = out(1, flags & F_MAIN), out(1, flags & F_MAIN)
+        color = out(3, (flags & F_COLOR) or shading in (2, 3))
+        normal, normal_raw = out(3, flags & F_FD), out(3, flags & F_FD)
+        deform, topo = out(3, flags & F_WARP), out(2, flags & F_WARP)
+        io.sdf, io.sigma, io.color, io.normal, io.normal_raw = ptr(sdf), ptr(sigma), ptr(color), ptr(normal), ptr(normal_raw)
+        io.deform, io.topo = ptr(deform), ptr(topo)
+        with _lib.timed('field_fwd_main' if flags & F_MAIN else 'field_fwd_aux'):
+            check(_lib.lib().mb_field_forward(_lib.C.byref(P), _lib.C.byref(io), stream()), 'field_forward')
+        ctx.cfg = cfg
+        ctx.shapes = (code0.shape, code1.shape, code2.shape)
+        ctx.save_for_backward(x, t, light, topo_in, arena, emb_sdf, emb_col, codes[0], codes[1], codes[2], beta_d, deform, topo, normal_raw)
+        ctx.set_materialize_grads(False)
+        return sdf, sigma, color, normal, normal_raw, deform, topo
+
+    @staticmethod
+    def backward(ctx, g_sdf, g_sigma, g_color, g_normal, g_raw, g_deform, g_topo):
+        flags, shading, ratio, n_levels, n_freq, offsets, bound, S, H = ctx.cfg
+        x, t, light, topo_in, arena, emb_sdf, emb_col, c0, c1, c2, beta_d, deform, topo, normal_raw = ctx.saved_tensors
+        M = x.shape[0]
+        codes = [c0, c1, c2]
+        P = packing.fill_descs(_lib.FieldParams())
+        P.arena = ptr(arena.detach())
+        P.emb_sdf, P.emb_col, P.offsets = ptr(emb_sdf.detach()), ptr(emb_col.detach()), ptr(offsets)
+        for i in range(3):
+            P.code[i] = codes[i].data_ptr()
+            P.code_len[i] = codes[i].shape[1]
+        P.beta = ptr(beta_d)
+        P.bound, P.two_bound, P.S, P.H = bound, float(2 * bound), S, H
+        P.n_levels, P.n_freq = n_levels, n_freq
+        io = _lib.FieldIO()
+        io.M, io.flags, io.shading, io.ratio = M, flags, shading, float(ratio)
+        io.x, io.t, io.light, io.topo_in = ptr(x), ptr(t), ptr(light), ptr(topo_in)
+
+        def cg(g):
+            return g.contiguous().float() if g is not None else None
+        g_sdf, g_sigma, g_color, g_normal, g_raw, g_deform, g_topo = map(cg, (g_sdf, g_sigma, g_color, g_normal, g_raw, g_deform, g_topo))
+        G = _lib.FieldGrads()
+        G.g_sdf, G.g_sigma, G.g_color, G.g_normal, G.g_normal_raw, G.g_deform, G.g_topo = map(ptr, (g_sdf, g_sigma, g_color, g_normal, g_raw, g_deform, g_topo))
+        G.deform, G.topo, G.normal_raw = ptr(deform), ptr(topo), ptr(normal_raw)
+        g_arena = torch.zeros_like(arena)
+        g_es = torch.zeros_like(emb_sdf)
+        g_ec = torch.zeros_like(emb_col)
+        g_codes = [torch.zeros_like(c) for c in codes]
+        g_beta = torch.zeros(1, device=x.device, dtype=torch.float32)
+        g_x = torch.empty_like(x)
+        g_topo_in = torch.empty_like(topo_in) if topo_in is not None else None
+        G.g_arena, G.g_emb_sdf, G.g_emb_col, G.g_beta, G.g_x, G.g_topo_in = map(ptr, (g_arena, g_es, g_ec, g_beta, g_x, g_topo_in))
+        for i in range(3):
+            G.g_code[i] = g_codes[i].data_ptr()
+        with _lib.timed('field_bwd_main' if flags & F_MAIN else 'field_bwd_aux'):
+            check(_lib.lib().mb_field_backward(_lib.C.byref(P), _lib.C.byref(io), _lib.C.byref(G), stream()), 'field_backward')
+        gc = [g.reshape(s) for g, s in zip(g_codes, ctx.shapes)]
+        return (None, g_x, None, None, g_topo_in, g_arena, g_es, g_ec, gc[0], gc[1], gc[2], g_beta.reshape(()))
+
+
+# ------------------------------------------------------------------------------------------------
+class scene_representation(nn.Module):
+    def __init__(self, config, bound, max_level=None, num_layers=3, num_layers_t=6, hidden_dim=64, hidden_dim_t=128,
+                 hidden_dim_tpo=128, num_layers_bg=2, geo_dim=32, deform_dim=16, hidden_dim_bg=32, amb_dim=2, num_frames=None,
+                 use_app=False, use_t=False, color_grid=True, use_joint=False, encode_topo=False, encode_deform=True):
+        super().__init__()
+        shipped = dict(num_layers=3, num_layers_t=6, hidden_dim=64, hidden_dim_t=128, hidden_dim_tpo=128, geo_dim=32,
+                       deform_dim=16, amb_dim=2, use_app=False, use_t=False, color_grid=True, use_joint=True,
+                       encode_topo=False, encode_deform=True)
+        given = dict(num_layers=num_layers, num_layers_t=num_layers_t, hidden_dim=hidden_dim, hidden_dim_t=hidden_dim_t,
+                     hidden_dim_tpo=hidden_dim_tpo, geo_dim=geo_dim, deform_dim=deform_dim, amb_dim=amb_dim, use_app=use_app,
+                     use_t=use_t, color_grid=color_grid, use_joint=use_joint, encode_topo=encode_topo, encode_deform=encode_deform)
+        if given != shipped:
+            diff = {k: v for k, v in given.items() if shipped[k] != v}
+            raise NotImplementedError(f'morpheus_b200 kernels are specialised for the configuration every MorpheuS yaml ships '
+                                      f'(morpheus.py:131-140, configs/*.yaml model section); unsupported overrides: {diff}')
+        self.config, self.bound, self.max_level = config, bound, max_level
+        self.num_layers, self.hidden_dim, self.geo_dim, self.num_frames = num_layers, hidden_dim, geo_dim, num_frames
+        self.use_t, self.use_app, self.use_joint, self.encode_topo, self.encode_deform = use_t, use_app, use_joint, encode_topo, encode_deform
+        self.pose_array = PoseArray(num_frames)
+        self.in_dim_amb = amb_dim
+        self.encoder_deform, self.in_dim_deform = get_encoder('frequency_torch', input_dim=3, multires=6)
+        self.deform_code, self.deform_dim = MultiCode([num_frames // 8, num_frames // 4, num_frames], deform_dim), 3 * deform_dim
+        self.deform_net = MLP(self.in_dim_deform + self.deform_dim, 3, hidden_dim_t, num_layers_t, bias=True)
+        self.topo_net = MLP(self.in_dim_deform + self.deform_dim, amb_dim, hidden_dim_tpo, num_layers_t, bias=True)
+        self.encoder, self.in_dim = get_encoder('hashgrid', input_dim=3, num_levels=16, log2_hashmap_size=15, desired_resolution=128)
+        self.encoder_c, self.in_dim_c = get_encoder('hashgrid', input_dim=3, num_levels=16, log2_hashmap_size=15, desired_resolution=128)
+        self.encoder_xyz, self.in_dim_xyz = get_encoder('frequency_torch', input_dim=3, multires=6)
+        self.sdf_net = MLP(self.in_dim + self.in_dim_amb + self.in_dim_xyz, 1 + geo_dim, hidden_dim, num_layers, bias=True,
+                           geo_init=True, geo_bias=0.4, weight_norm=False)
+        self.color_net = MLP(self.in_dim_c + geo_dim, 3, hidden_dim, num_layers, bias=True)
+        if self.config['model']['bg_radius'] > 0:
+            self.encoder_bg, self.in_dim_bg = get_encoder('frequency_torch', input_dim=3, multires=6)
+            self.encoder_bg_t, self.in_dim_bg_t = get_encoder('frequency_torch', input_dim=1, multires=6)
+            self.bg_net = MLP(self.in_dim_bg + self.in_dim_bg_t, 3, hidden_dim_bg, num_layers_bg, bias=True)
+        self.sdf2density = LaplaceDensity({'beta': 0.1})
+        self._arena_cache = None
+
+    # -- packed parameters ----------------------------------------------------------------------------
+    def packed_arena(self):
+        """Flat effective-weight arena (differentiable).  Rebuilt per call while training; cached under no_grad
+        until `invalidate()` (eval renders, occupancy refresh)."""
+        if not torch.is_grad_enabled() and self._arena_cache is not None:
+            return self._arena_cache
+        arena = packing.pack({'deform': self.deform_net.effective(), 'topo': self.topo_net.effective(),
+                              'sdf': self.sdf_net.effective(), 'color': self.color_net.effective()})
+        if not torch.is_grad_enabled():
+            self._arena_cache = arena
+        return arena
+
+    def invalidate(self):
+        self._arena_cache = None
+
+    def train(self, mode=True):
+        self._arena_cache = None
+        return super().train(mode)
+
+    def _levels(self):
+        L = 16
+        n_levels = L if self.max_level is None else max(min(int(math.ceil(self.max_level * L)), L), 1)   # grid.py:42
+        n_freq = 6 if self.max_level is None else int(self.max_level * 6)                                 # encodings.py:37-40
+        return n_levels, n_freq
+
+    def _query(self, x, t, flags, shading=0, ratio=1.0, light=None, topo_in=None, arena=None):
+        if x.shape[0] == 0:
+            raise RuntimeError('morpheus_b200: empty query (the reference would crash at morpheus.py:701 as well)')
+        n_levels, n_freq = self._levels()
+        enc = self.encoder
+        cfg = (int(flags), int(shading), float(ratio), n_levels, n_freq, enc.offsets, float(self.bound),
+               float(np.log2(enc.per_level_scale)), int(enc.base_resolution))
+        if arena is None:
+            arena = self.packed_arena()
+        v = self.deform_code.volumes
+        return _FieldQuery.apply(cfg, x, t, light, topo_in, arena, self.encoder.embeddings, self.encoder_c.embeddings,
+                                 v[0], v[1], v[2], self.sdf2density.get_beta())
+
+    # -- reference API --------------------------------------------------------------------------------
+    def get_deform_code(self, t, app=False):
+        return self.deform_code.sample(t)
+
+    def get_RT(self, frame_ids):
+        frame_ids = frame_ids.squeeze()
+        return self.pose_array.get_rotation_matrices(frame_ids), self.pose_array.get_translations(frame_ids)
+
+    def warp(self, x, t):
+        """model.py:412-437 -> (deform, topo, app_code=None)"""
+        out = self._query(x, t, F_WARP)
+        return out[5], out[6], None
+
+    def get_topo(self, x, t):
+        return self.warp(x, t)[1]
+
+    def get_sigma_albedo(self, x, topo=None, app_code=None, return_color=True):
+        """model.py:273-307"""
+        flags = F_MAIN | (F_COLOR if return_color else 0) | (F_TOPO_IN if topo is not None else 0)
+        out = self._query(x, None, flags, topo_in=topo)
+        return out[0], out[1], out[2]
+
+    def finite_difference_normal(self, x, epsilon=2e-3, topo=None):
+        assert abs(epsilon - 2e-3) < 1e-12, 'the kernel is specialised for epsilon = 2e-3 (model.py:367)'
+        out = self._query(x, None, F_FD | (F_TOPO_IN if topo is not None else 0), topo_in=topo)
+        return out[4]
+
+    def normal(self, x, t=None, cano=False, topo=None):
+        """model.py:387-398 -> (normal, normal_raw)"""
+        if t is not None and not cano:
+            out = self._query(x, t, F_WARP | F_FD | F_FD_WARPED)
+        else:
+            out = self._query(x, None, F_FD | (F_TOPO_IN if topo is not None else 0), topo_in=topo)
+        return out[3], out[4]
+
+    def background(self, d, t):
+        """model.py:400-410 (never reached with the shipped flags); plain torch."""
+        h = torch.cat([self.encoder_bg(d), self.encoder_bg_t(t, max_level=self.max_level)], dim=-1)
+        return torch.sigmoid(self.bg_net(h))
+
+    def pose_optimisation(self, rays_o, rays_d, frame_ids):
+        """model.py:335-346"""
+        frame_ids = frame_ids.squeeze()
+        R = self.pose_array.get_rotation_matrices(frame_ids)
+        tr = self.pose_array.get_translations(frame_ids)
+        return rays_o + tr, torch.sum(rays_d[..., None, :] * R, -1)
+
+    def density(self, x, t=None, cano=False, allow_shape=False, return_color=True):
+        """model.py:439-481"""
+        if cano or t is None:
+            out = self._query(x, None, F_MAIN | (F_COLOR if return_color else 0))
+        else:
+            if isinstance(t, float):
+                t = t * torch.ones(x.shape[0], 1, device=x.device)
+            if x.shape[0] != t.shape[0]:
+                if not allow_shape:
+                    raise Exception('Shape inconsistent!!!')
+                t = t[0, 0] * torch.ones(x.shape[0], 1, device=x.device)
+            out = self._query(x, t, F_WARP | F_MAIN | (F_COLOR if return_color else 0))
+        return {'sdf': out[0], 'sigma': out[1], 'albedo': out[2]}
+
+    def forward(self, x, t, light_dir=None, ratio=1, shading='albedo', cano=False, return_color=True):
+        """model.py:483-533 -> (sdf, sigma, color, normal, deform, normal_raw)"""
+        flags = F_MAIN | (F_COLOR if return_color else 0) | (0 if cano else F_WARP)
+        if shading == 'albedo':
+            out = self._query(x, None if cano else t, flags)
+            return out[0], out[1], out[2], None, out[5], None
+        out = self._query(x, None if cano else t, flags | F_FD, shading=SHADE[shading], ratio=ratio, light=light_dir)
+        return out[0], out[1], out[2], out[3], out[5], out[4]
+
+    def get_params_all(self, lr):
+        """model.py:309-333 (same group names; morpheus.py:494-516 looks them up by name)"""
+        params = [
+            {'name': 'encoder_sdf', 'params': self.encoder.parameters(), 'lr': lr},
+            {'name': 'encoder_color', 'params': self.encoder_c.parameters(), 'lr': lr},
+            {'name': 'decoder_sdf', 'params': self.sdf_net.parameters(), 'lr': lr},
+            {'name': 'decoder_topo', 'params': self.topo_net.parameters(), 'lr': lr},
+            {'name': 'decoder_color', 'params': self.color_net.parameters(), 'lr': lr},
+            {'name': 'density', 'params': self.sdf2density.parameters(), 'lr': lr / 2.},
+            {'name': 'decoder_deform', 'params': self.deform_net.parameters(), 'lr': lr},
+            {'name': 'code_deform', 'params': self.deform_code.parameters(), 'lr': lr},
+            {'name': 'pose', 'params': self.pose_array.parameters(), 'lr': lr / 10.},
+        ]
+        if self.config['model']['bg_radius'] > 0:
+            params.append({'name': 'decoder_bg', 'params': self.bg_net.parameters(), 'lr': lr})
+        return params

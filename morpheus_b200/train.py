@@ -1,0 +1,111 @@
+"""Per-iteration training step around render_rays: loss heads that consume the render outputs
+(morpheus.py:946-983 get_real_view_render_loss, :985-999 sdf part of get_real_view_point_loss,
+:1090-1145 get_regularization_loss -- the terms active with the shipped weights),
+a flat parameter/gradient arena with one fused Adam launch (morpheus.py:154-155: Adam(betas=(.9,.99),
+eps=1e-15) over the named groups of models/model.py:313-324), and the data-parallel exchange: one
+NCCL all-reduce of the flat gradient arena per step (the reference is single-GPU).
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import check, ptr, stream
+
+DEFAULT_TRAIN_CFG = {  # configs/snoopy.yaml:40-94 (only what the step reads)
+    'rgb_weight': 5.0, 'mask_weight': 0.5, 'depth_weight': 0.1, 'sdf_weight': 10.0, 'fs_weight': 0.0,
+    'normal_smooth_3d': 0.1, 'smoothness_std': 0.005, 'topo_none': True, 'normal_dir': False, 'code_reg': 0.5,
+    'beta_weight': 0.1, 'ori_weight': 0.01, 'trunc': 0.1, 'lr': 5e-4,
+}
+
+
+def real_view_loss(out, batch, model, tr):
+    """rgb MSE x5 + mask BCE x.5 + masked depth MSE x.1 (morpheus.py:946-983) + sdf band loss x10 (:991-992)
+    + normal_smooth_3d x.1 + code_reg x.5 + beta x.1 (:1116-1142)."""
+    pred_rgb = out['image'].reshape(-1, 3)
+    pred_depth = out['depth'].reshape(-1)
+    pred_mask = out['weights_sum'].reshape(-1)
+    gt_rgb, gt_depth, gt_mask = batch['rgb'], batch['depth'].reshape(-1), batch['mask'].reshape(-1)
+    loss = tr['rgb_weight'] * F.mse_loss(pred_rgb, gt_rgb)
+    loss = loss + tr['mask_weight'] * F.binary_cross_entropy(pred_mask.clip(1e-5, 1.0 - 1e-5), gt_mask.float())
+    xyz = batch['rays_o'].reshape(-1, 3) + gt_depth[:, None] * batch['rays_d'].reshape(-1, 3)
+    depth_mask = ((gt_depth > 0) & (xyz.norm(dim=-1) <= 1.1) & (gt_mask > 0.5)).float()
+    loss = loss + tr['depth_weight'] * F.mse_loss(pred_depth * depth_mask, gt_depth * depth_mask)
+    if 'sdf_loss' in out:
+        loss = loss + tr['sdf_weight'] * out['sdf_loss'] + tr['fs_weight'] * out['fs_loss']
+    if 'loss_normal_perturb' in out:
+        loss = loss + tr['normal_smooth_3d'] * out['loss_normal_perturb']
+    if 'loss_code' in out:
+        loss = loss + tr['code_reg'] * out['loss_code']
+    loss = loss + tr['beta_weight'] * torch.mean(model.sdf2density.get_beta())
+    return loss
+
+
+class FlatAdam:
+    """All trainable parameters re-homed into ONE flat fp32 buffer (and their .grad into one flat gradient
+    buffer), so a step is: zero one buffer, one all-reduce, one fused Adam launch (csrc/sampler.cu:adam_kernel).
+    Per-group learning rates follow get_params_all() (models/model.py:313-324)."""
+
+    def __init__(self, model, lr, betas=(0.9, 0.99), eps=1e-15):
+        groups = model.get_params_all(lr)
+        plist, gid, lrs = [], [], []
+        for gi, g in enumerate(groups):
+            lrs.append(g['lr'])
+            for p in g['params']:
+                plist.append(p)
+                gid.append(gi)
+        n = sum(p.numel() for p in plist)
+        dev = plist[0].device
+        self.flat = torch.empty(n, device=dev)
+        self.grad = torch.zeros(n, device=dev)
+        self.m = torch.zeros(n, device=dev)
+        self.v = torch.zeros(n, device=dev)
+        self.group_id = torch.empty(n, dtype=torch.uint8, device=dev)
+        off = 0
+        for p, gi in zip(plist, gid):
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view(p.shape)
+            p.grad = self.grad[off:off + k].view(p.shape)
+            self.group_id[off:off + k] = gi
+            off += k
+        self.group_names = [g['name'] for g in groups]
+        self.group_lr = torch.tensor(lrs, device=dev, dtype=torch.float32)
+        self.betas, self.eps, self.t, self.n = betas, eps, 0, n
+        self.params = plist
+
+    def set_group_lr(self, name, lr):
+        self.group_lr[self.group_names.index(name)] = lr
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def all_reduce(self):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+
+    def step(self):
+        self.t += 1
+        with _lib.timed('adam'):
+          check(_lib.lib().mb_adam_step(ptr(self.flat), ptr(self.grad), ptr(self.m), ptr(self.v), ptr(self.group_id), ptr(self.group_lr),
+                                      C.c_uint64(self.n), C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
+                                      self.t, stream()), 'adam_step')
+
+
+def train_step(renderer, opt, batch, tr, world_size=1, shading='albedo_normal', samples=None):
+    """One real-view optimiser step (morpheus.py:1147-1236 + :1415-1424) on this rank's shard of the ray batch.
+    Loss terms are means over the GLOBAL batch: every rank divides by world_size so that the summed
+    all-reduce equals the single-GPU gradient."""
+    model = renderer.model
+    opt.zero_grad()
+    out = renderer.render_rays(batch['rays_o'], batch['rays_d'], batch['rays_t'], batch['rays_id'], bg_color=batch['bg'],
+                               shading=shading, real_view=True, rays_depth=batch['depth'], rays_mask=batch['mask'],
+                               optimize_pose=True, samples=samples)
+    loss = real_view_loss(out, batch, model, tr)
+    (loss / world_size).backward()
+    opt.all_reduce()
+    opt.step()
+    model.invalidate()
+    return loss.detach()

@@ -203,12 +203,14 @@ class SceneOracle:
         return rays_o + tr, (rays_d[..., None, :] * R).sum(-1)
 
 
-def init_reference_like_state(num_frames=200, seed=0, dtype=torch.float32, emb_scale=1e-4, randomize=False):
+def init_reference_like_state(num_frames=200, seed=0, dtype=torch.float32, emb_scale=1e-4, randomize=False, sphere=False):
     """Seeded state_dict with the reference's shapes/names.  With
     randomize=False it follows the reference initialisers (geometric init for sdf_net,
     models/decoders.py:24-43; weight_norm g=||v||; U(-1e-4,1e-4) tables, grid.py:145-147);
     randomize=True perturbs everything (g, biases, beta, poses, big tables) so parity tests see
-    a 'trained-like' generic model."""
+    a 'trained-like' generic model.  sphere=True (with randomize=True) keeps the geometric-init SDF net untouched
+    (sdf ~ |x| - 0.4: rays cross a surface, so sigma / weights / depth are well-conditioned, SURVEY.md 8d "trained-like
+    sphere SDF") and shrinks the deformation output so the sphere survives the warp."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
 
@@ -242,7 +244,7 @@ def init_reference_like_state(num_frames=200, seed=0, dtype=torch.float32, emb_s
             W[:, :3] = torch.randn(dims[l + 1], 3, generator=g) * (math.sqrt(2) / math.sqrt(dims[l + 1]))
         else:
             W = torch.randn(dims[l + 1], dims[l], generator=g) * (math.sqrt(2) / math.sqrt(dims[l + 1]))
-        if randomize:
+        if randomize and not sphere:
             W = W + 0.05 * torch.randn(W.shape, generator=g)
             b = b + 0.05 * torch.randn(b.shape, generator=g)
         sd[f'sdf_net.net.{l}.weight'] = W
@@ -259,6 +261,8 @@ def init_reference_like_state(num_frames=200, seed=0, dtype=torch.float32, emb_s
     for enc in ('encoder', 'encoder_c'):
         sd[enc + '.offsets'] = offs.clone()
         sd[enc + '.embeddings'] = (torch.rand(int(offs[-1]), 2, generator=g) * 2 - 1) * emb_scale
-    sd['sdf2density.beta'] = torch.tensor(0.1 if not randomize else 0.037)
+    sd['sdf2density.beta'] = torch.tensor(0.1 if not randomize else (0.05 if sphere else 0.037))
+    if sphere:
+        sd['deform_net.net.5.weight_g'] = sd['deform_net.net.5.weight_g'] * 0.2
     sd['pose_array.data'] = torch.zeros(num_frames, 6) if not randomize else 0.02 * torch.randn(num_frames, 6, generator=g)
     return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}

@@ -1,0 +1,403 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every test drives the CUDA product path
+through the C ABI (morpheus_b200/libmorpheus_b200.so) and compares it with
+  * the CPU oracle (oracle/) on the same seeded inputs,
+  * the golden vectors produced by the unmodified reference Python (tests/golden/scene_*.npz),
+  * and, for the grid encoder, the reference CUDA kernel itself (oracle/_ref, built from
+    /root/reference/external/encoders/gridencoder/src by oracle/build_ref.sh) -- bit for bit.
+Tolerances: integer/index outputs bit-exact; fp32 outputs within the stated rel/abs bounds
+(BASELINE.json north_star: rendered RGB/depth <= 1e-4 relative L2).
+"""
+import glob
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CONFIG = {'model': {'bg_radius': 1.4, 'activation': 'exp'}}
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def cpu(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope='module')
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    return torch.device('cuda:0')
+
+
+def make_model(sd, max_level, dev):
+    from morpheus_b200.model import scene_representation
+    m = scene_representation(CONFIG, 1.01, num_frames=200, deform_dim=16, use_app=False, use_t=False, amb_dim=2,
+                             color_grid=True, use_joint=True, encode_topo=False)
+    m.load_state_dict(sd, strict=True)   # reference state_dict keys load unchanged
+    m.max_level = max_level
+    return m.to(dev)
+
+
+def load_case(golden_dir, tag):
+    from oracle.fields import init_reference_like_state
+    z = np.load(os.path.join(golden_dir, f'scene_{tag}.npz'))
+    ml = float(z['max_level'])
+    sd = init_reference_like_state(200, seed=int(z['seed']), randomize=bool(z['randomize']), emb_scale=float(z['emb_scale']))
+    return z, sd, (None if ml < 0 else ml)
+
+
+# ------------------------------------------------------------------------------------------------
+# grid encoder
+# ------------------------------------------------------------------------------------------------
+def _grid_inputs(B, seed, dev):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, 3, generator=g)
+    x[0] = torch.tensor([0.0, 0.0, 0.0]); x[1] = torch.tensor([1.0, 1.0, 1.0]); x[2] = torch.tensor([0.5, 0.5, 0.5])
+    x[3] = torch.tensor([1.0001, 0.2, 0.3]); x[4] = torch.tensor([-1e-6, 0.2, 0.3])      # out of bounds
+    x[5] = torch.tensor([31.5 / 32, 0.5 / 32, 16.5 / 32])                                  # exactly on cell centres
+    x[6] = x[7] + torch.tensor([2e-3 / 2.02, 0, 0])                                        # FD-offset pair
+    return x
+
+
+@pytest.mark.parametrize('max_level_frac', [None, 0.5, 0.53])
+@pytest.mark.parametrize('emb_scale', [1e-4, 1.0])
+def test_grid_encode_vs_oracle(dev, max_level_frac, emb_scale):
+    from morpheus_b200.gridencoder import GridEncoder
+    from oracle import grid as og
+    B = 1000
+    enc = GridEncoder(input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=15, desired_resolution=128).to(dev)
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        enc.embeddings.copy_(((torch.rand(enc.embeddings.shape, generator=g) * 2 - 1) * emb_scale).to(dev))
+    x01 = _grid_inputs(B, 5, dev)
+    xw = (x01 * 2.02 - 1.01).to(dev).requires_grad_(True)
+    out = enc(xw, bound=1.01, max_level=max_level_frac)
+    gout = torch.randn(out.shape, generator=g).to(dev)
+    out.backward(gout)
+    # oracle on the exact same [0,1] inputs the kernel saw
+    u = cpu((xw.detach() + 1.01) / (2 * 1.01))
+    S = float(np.log2(enc.per_level_scale))
+    ml = og.resolve_max_level(max_level_frac, 16)
+    o_ref, dydx_ref = og.grid_encode_forward(u, cpu(enc.embeddings), cpu(enc.offsets), ml, S, 16, True)
+    o_ref = np.transpose(o_ref, (1, 0, 2)).reshape(B, 32)
+    np.testing.assert_allclose(cpu(out), o_ref, rtol=1e-6, atol=1e-7 * emb_scale)
+    g_lbc = np.ascontiguousarray(np.transpose(cpu(gout).reshape(B, 16, 2), (1, 0, 2)))
+    ge_ref, gi_ref = og.grid_encode_backward(g_lbc, u, cpu(enc.embeddings), cpu(enc.offsets), ml, S, 16, dydx_ref)
+    assert rel_l2(cpu(enc.embeddings.grad), ge_ref) < 1e-5
+    assert rel_l2(cpu(xw.grad), gi_ref / 2.02) < 1e-5
+
+
+def _load_ref_backend():
+    paths = glob.glob(os.path.join(ROOT, 'oracle', '_ref', '_gridencoder_ref*.so'))
+    if not paths:
+        return None
+    spec = importlib.util.spec_from_file_location('_gridencoder_ref', paths[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize('calc_dydx', [False, True])
+def test_grid_encode_bit_exact_vs_reference_kernel(dev, calc_dydx):
+    """Our kernel against the reference CUDA kernel compiled from the reference sources (oracle/_ref)."""
+    ref = _load_ref_backend()
+    if ref is None:
+        pytest.skip('oracle/_ref not built (needs /root/reference at build time)')
+    from morpheus_b200.gridencoder import _backend as ours
+    from oracle import grid as og
+    B, D, C, L, H = 20000, 3, 2, 16, 16
+    S = float(np.log2(og.per_level_scale()))
+    offsets = torch.from_numpy(og.make_offsets()).to(dev)
+    g = torch.Generator().manual_seed(11)
+    emb = ((torch.rand(int(offsets[-1]), C, generator=g) * 2 - 1)).to(dev)
+    x = _grid_inputs(B, 9, dev).to(dev)
+    for max_level in (16, 9):
+        outs, dys = [], []
+        for be in (ref, ours):
+            o = torch.zeros(L, B, C, device=dev)
+            dy = torch.zeros(B, L * D * C, device=dev) if calc_dydx else None
+            be.grid_encode_forward(x, emb, offsets, o, B, D, C, L, max_level, S, H, dy, 0, False, 0)
+            outs.append(o); dys.append(dy)
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0], outs[1]), f'forward differs: max abs {(outs[0] - outs[1]).abs().max().item()}'
+        if calc_dydx:
+            assert torch.equal(dys[0], dys[1]), f'dy_dx differs: max abs {(dys[0] - dys[1]).abs().max().item()}'
+            grad = torch.randn(L, B, C, generator=g).to(dev)
+            res = []
+            for be in (ref, ours):
+                ge = torch.zeros_like(emb)
+                gi = torch.zeros(B, D, device=dev)
+                be.grid_encode_backward(grad, x, emb, offsets, ge, B, D, C, L, max_level, S, H, dys[0], gi, 0, False, 0)
+                res.append((ge, gi))
+            torch.cuda.synchronize()
+            assert torch.equal(res[0][1], res[1][1]), 'grad_inputs differs'
+            assert rel_l2(cpu(res[1][0]), cpu(res[0][0])) < 1e-6   # atomics: order differs
+
+
+def test_grid_encode_errors(dev):
+    from morpheus_b200.gridencoder import _backend as ours
+    x = torch.rand(8, 5, device=dev)
+    emb = torch.rand(64, 2, device=dev)
+    off = torch.tensor([0, 64], dtype=torch.int32, device=dev)
+    out = torch.zeros(1, 8, 2, device=dev)
+    with pytest.raises(RuntimeError):   # reference: std::runtime_error "D must be 2, 3, 4 or 5" -> we support {2,3}
+        ours.grid_encode_forward(x, emb, off, out, 8, 5, 2, 1, 1, 0.0, 16, None, 0, False, 0)
+    with pytest.raises(RuntimeError):
+        ours.grid_encode_forward(x.cpu(), emb, off, out, 8, 3, 2, 1, 1, 0.0, 16, None, 0, False, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# scene model: forward in every shading mode, vs golden (reference Python) and oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('tag', ['init_full', 'rand_c2f', 'rand_full'])
+def test_scene_forward_vs_reference_golden(dev, golden_dir, tag):
+    z, sd, ml = load_case(golden_dir, tag)
+    m = make_model(sd, ml, dev).eval()
+    x, t, light = (torch.from_numpy(z[k]).to(dev) for k in ('x', 't', 'light'))
+
+    def close(a, name, rtol=1e-4, atol=1e-5):
+        np.testing.assert_allclose(cpu(a), z[name], rtol=rtol, atol=atol, err_msg=name)
+    with torch.no_grad():
+        for shading, ratio in (('albedo', 1.0), ('albedo_normal', 1.0), ('lambertian', 0.3), ('textureless', 0.55), ('normal', 1.0)):
+            sdf, sigma, color, normal, deform, raw = m(x, t, light, ratio=ratio, shading=shading)
+            close(sdf, f'{shading}.sdf'); close(sigma, f'{shading}.sigma', rtol=5e-4, atol=1e-4); close(deform, f'{shading}.deform')
+            shaded = shading in ('lambertian', 'textureless', 'normal')
+            close(color, f'{shading}.color', rtol=2e-3 if shaded else 1e-4, atol=5e-4 if shaded else 1e-5)
+            if normal is not None:
+                close(raw, f'{shading}.normal_raw', rtol=2e-3, atol=5e-4)   # FD of fp32 values: cancellation noise
+                close(normal, f'{shading}.normal', rtol=2e-3, atol=5e-4)
+        d = m.density(x, t)
+        close(d['sdf'], 'density.sdf'); close(d['albedo'], 'density.albedo')
+        d = m.density(x, None)
+        close(d['sdf'], 'density_cano.sdf'); close(d['albedo'], 'density_cano.albedo')
+        d = m.density(x, t[:3], allow_shape=True, return_color=False)
+        close(d['sigma'], 'density_allow_shape.sigma', rtol=5e-4, atol=1e-4)
+        n, raw = m.normal(x, t=t)
+        close(raw, 'normal_warped.raw', rtol=2e-3, atol=5e-4)
+        n, raw = m.normal(x, topo=None)
+        close(raw, 'normal_cano.raw', rtol=2e-3, atol=5e-4)
+        deform, topo, _ = m.warp(x, t)
+        close(deform, 'warp.deform'); close(topo, 'warp.topo')
+        close(m.get_deform_code(t), 'code', rtol=1e-5, atol=1e-6)
+        close(m.background(light, t), 'background')
+        o2, d2 = m.pose_optimisation(x, light, torch.from_numpy(z['pose.ids']).to(dev))
+        close(o2, 'pose.o', rtol=1e-5); close(d2, 'pose.d', rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('tag', ['init_full', 'rand_c2f', 'rand_full'])
+def test_scene_backward_vs_reference_golden(dev, golden_dir, tag):
+    """Param / input gradients of the fused backward kernel vs autograd through the unmodified reference."""
+    z, sd, ml = load_case(golden_dir, tag)
+    m = make_model(sd, ml, dev).train()
+    x, t, light = (torch.from_numpy(z[k]).to(dev) for k in ('x', 't', 'light'))
+    M = x.shape[0]
+    xg = x.clone().requires_grad_(True)
+    sdf, sigma, color, normal, deform, raw = m(xg, t, light, ratio=1.0, shading='albedo_normal')
+    g = torch.Generator().manual_seed(77)
+    r = [torch.randn(M, generator=g), torch.randn(M, generator=g), torch.randn(M, 3, generator=g), torch.randn(M, 3, generator=g),
+         torch.randn(M, 3, generator=g)]
+    r = [v.to(dev) for v in r]
+    loss = (sdf * r[0]).sum() + (sigma * r[1]).sum() * 1e-2 + (color * r[2]).sum() + (normal * r[3]).sum() + (deform * r[4]).sum()
+    loss.backward()
+    bad = []
+    errs = {'x': rel_l2(cpu(xg.grad), z['grad.x'])}
+    for name, p in m.named_parameters():
+        key = 'grad.' + name
+        if key in z.files and p.grad is not None and np.abs(z[key]).max() > 0:
+            errs[name] = rel_l2(cpu(p.grad), z[key])
+    for k, e in errs.items():
+        # beta: with |sdf| >> beta the reference's own fp32 `0.5 + 0.5*expm1(-|s|/beta)` cancels catastrophically (its
+        # autograd value is ~1% off the fp64 value, see DESIGN.md "numerics"); the well-conditioned beta-gradient check
+        # is test_scene_forward_backward_vs_oracle_large.
+        if e > (5e-2 if k == 'sdf2density.beta' else 2e-3):
+            bad.append((k, e))
+    assert not bad, f'gradient mismatch: {bad}\nall: {errs}'
+
+
+def test_scene_forward_backward_vs_oracle_large(dev):
+    """Bigger ragged batch (partial last tile, two frames) against the CPU oracle incl. autograd."""
+    from oracle.fields import SceneOracle, init_reference_like_state
+    sd = init_reference_like_state(200, seed=5, randomize=True, emb_scale=0.3)
+    sd['sdf2density.beta'] = torch.tensor(0.6)     # |sdf| ~ beta: well-conditioned sigma / d sigma / d beta
+    M = 1000 + 37
+    g = torch.Generator().manual_seed(123)
+    x = (torch.rand(M, 3, generator=g) * 2 - 1) * 0.95
+    t = torch.full((M, 1), 63.0 / 200)
+    light = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1)
+    w = [torch.randn(M, generator=g), torch.randn(M, 3, generator=g), torch.randn(M, 3, generator=g)]
+    # oracle
+    sdo = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    sc = SceneOracle(sdo, 1.01, 200, 0.77)
+    xo = x.clone().requires_grad_(True)
+    so, sgo, co, no, do, ro = sc.forward(xo, t, light, ratio=0.4, shading='lambertian')
+    lo = (so * w[0]).sum() + (co * w[1]).sum() + (no * w[2]).sum() + (sgo * w[0]).sum()
+    lo.backward()
+    # ours
+    m = make_model(sd, 0.77, dev).train()
+    xd = x.to(dev).requires_grad_(True)
+    s, sg, c, n, d, r = m(xd, t.to(dev), light.to(dev), ratio=0.4, shading='lambertian')
+    l = (s * w[0].to(dev)).sum() + (c * w[1].to(dev)).sum() + (n * w[2].to(dev)).sum() + (sg * w[0].to(dev)).sum()
+    l.backward()
+    assert rel_l2(cpu(s), cpu(so)) < 1e-5
+    assert rel_l2(cpu(sg), cpu(sgo)) < 1e-4
+    assert rel_l2(cpu(c), cpu(co)) < 1e-3
+    assert rel_l2(cpu(d), cpu(do)) < 1e-5
+    errs = {'x': rel_l2(cpu(xd.grad), cpu(xo.grad))}
+    for name, p in m.named_parameters():
+        if name in sdo and sdo[name].grad is not None and p.grad is not None and float(sdo[name].grad.abs().max()) > 0:
+            errs[name] = rel_l2(cpu(p.grad), cpu(sdo[name].grad))
+    bad = {k: e for k, e in errs.items() if e > 5e-3}
+    assert not bad, f'{bad}\nall: {errs}'
+
+
+# ------------------------------------------------------------------------------------------------
+# sampling + compositing
+# ------------------------------------------------------------------------------------------------
+def _rays(N, seed):
+    from oracle.render import camera_dirs, look_at_pose, rays_from_pose
+    g = torch.Generator().manual_seed(seed)
+    c2w = look_at_pose(70.0, 35.0, 2.5)
+    dirs = camera_dirs(360, 360, 517.0, 517.0, 180.0, 180.0).reshape(-1, 3)
+    idx = torch.randint(0, dirs.shape[0], (N,), generator=g)
+    o, d = rays_from_pose(dirs[idx], c2w)
+    return o.contiguous(), d.contiguous(), g
+
+
+def test_sampler_vs_oracle(dev):
+    from morpheus_b200.nerfacc_compat import OccGridEstimator
+    from oracle.render import sample_occgrid
+    N = 64
+    o, d, g = _rays(N, 1)
+    aabb = torch.tensor([-1.01, -1.01, -1.01, 1.01, 1.01, 1.01])
+    est = OccGridEstimator(aabb, resolution=128).to(dev)
+    r = torch.arange(128)
+    cx, cy, cz = torch.meshgrid(r, r, r, indexing='ij')
+    centre = (torch.stack([cx, cy, cz], -1).float() + 0.5) / 128 * 2.02 - 1.01
+    binaries = (centre.norm(dim=-1) < 0.6) & (centre.norm(dim=-1) > 0.3)     # spherical shell: ragged, some empty rays
+    est.binaries = binaries[None].to(dev)
+    jitter = torch.rand(N, generator=g)
+    ri, t0, t1 = est.sampling(o.to(dev), d.to(dev), render_step_size=0.01, stratified=True, jitter=jitter.to(dev))
+    ri_o, t0_o, t1_o = sample_occgrid(o, d, binaries, aabb, 0.01, jitter)
+    assert ri.dtype == torch.int64
+    assert torch.equal(ri.cpu(), ri_o)                       # index work: bit-exact
+    np.testing.assert_array_equal(cpu(t0), t0_o.numpy())     # same float32 lattice
+    np.testing.assert_array_equal(cpu(t1), t1_o.numpy())
+    assert bool((ri[1:] >= ri[:-1]).all())
+
+
+def test_composite_vs_oracle(dev):
+    from morpheus_b200 import nerfacc_compat as nf
+    from oracle import render as orr
+    g = torch.Generator().manual_seed(2)
+    counts = torch.tensor([0, 5, 1, 0, 77, 33, 0, 130, 2, 0])
+    N = counts.numel()
+    ri = torch.arange(N).repeat_interleave(counts)
+    M = ri.numel()
+    t0 = torch.rand(M, generator=g) * 3
+    t1 = t0 + 0.01 + torch.rand(M, generator=g) * 0.02
+    sig = (torch.rand(M, generator=g) * 30).requires_grad_(True)
+    rgb = torch.rand(M, 3, generator=g).requires_grad_(True)
+    gw, go, gd, gc = torch.randn(M, generator=g), torch.randn(N, 1, generator=g), torch.randn(N, 1, generator=g), torch.randn(N, 3, generator=g)
+    w, _, _ = orr.render_weight_from_density(t0, t1, sig, ri, N)
+    op = orr.accumulate_along_rays(w, None, ri, N)
+    dp = orr.accumulate_along_rays(w, ((t0 + t1) / 2)[:, None], ri, N)
+    cl = orr.accumulate_along_rays(w, rgb, ri, N)
+    ((w * gw).sum() + (op * go).sum() + (dp * gd).sum() + (cl * gc).sum()).backward()
+    sig_d = sig.detach().to(dev).requires_grad_(True)
+    rgb_d = rgb.detach().to(dev).requires_grad_(True)
+    w2, o2, d2, c2 = nf.composite(sig_d, rgb_d, t0.to(dev), t1.to(dev), ri.to(dev), N)
+    ((w2 * gw.to(dev)).sum() + (o2 * go[:, 0].to(dev)).sum() + (d2 * gd[:, 0].to(dev)).sum() + (c2 * gc.to(dev)).sum()).backward()
+    np.testing.assert_allclose(cpu(w2), cpu(w), rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(cpu(o2), cpu(op)[:, 0], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(cpu(d2), cpu(dp)[:, 0], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(cpu(c2), cpu(cl), rtol=2e-5, atol=1e-6)
+    assert rel_l2(cpu(sig_d.grad), cpu(sig.grad)) < 1e-4
+    assert rel_l2(cpu(rgb_d.grad), cpu(rgb.grad)) < 1e-5
+    # API-compatible split calls
+    w3, tr3, al3 = nf.render_weight_from_density(t0.to(dev), t1.to(dev), sig_d.detach(), ray_indices=ri.to(dev), n_rays=N)
+    np.testing.assert_allclose(cpu(w3), cpu(w), rtol=2e-5, atol=1e-7)
+    acc = nf.accumulate_along_rays(w3, values=rgb_d.detach(), ray_indices=ri.to(dev), n_rays=N)
+    np.testing.assert_allclose(cpu(acc), cpu(cl), rtol=2e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# end to end: render_rays (BASELINE cfg-1: 256 rays x 64 samples, SDS off) vs the oracle
+# ------------------------------------------------------------------------------------------------
+def test_render_rays_cfg1_vs_oracle(dev):
+    from morpheus_b200.nerfacc_compat import OccGridEstimator
+    from morpheus_b200.render import Renderer
+    from oracle import render as orr
+    from oracle.fields import SceneOracle, init_reference_like_state
+    N, S = 256, 64
+    sd = init_reference_like_state(200, seed=7, randomize=True, emb_scale=0.02, sphere=True)
+    o, d, g = _rays(N, 3)
+    aabb = torch.tensor([-1.01, -1.01, -1.01, 1.01, 1.01, 1.01])
+    jitter = torch.rand(N, generator=g)
+    samples = orr.sample_uniform(o, d, aabb, S, jitter)
+    t = torch.full((1, N, 1), 41.0 / 200)
+    ids = torch.full((1, N, 1), 41, dtype=torch.long)
+    bg = torch.rand(N, 3, generator=g)
+    sc = SceneOracle(sd, 1.01, 200, 0.8)
+    with torch.no_grad():
+        ref = orr.render_rays(sc, o[None], d[None], t, ids, samples, bg_color=bg, shading='albedo')
+    m = make_model(sd, 0.8, dev).eval()
+    cfg = {'render': {'step_size': 0.01}, 'model': CONFIG['model'], 'train': {}}
+    R = Renderer(m, OccGridEstimator(aabb, 128).to(dev), cfg, 200)
+    with torch.no_grad():
+        out = R.render_rays(o[None].to(dev), d[None].to(dev), t.to(dev), ids.to(dev), bg_color=bg.to(dev), shading='albedo',
+                            samples=tuple(s.to(dev) for s in samples))
+    e_img = rel_l2(cpu(out['image']).reshape(-1, 3), cpu(ref['image']))
+    e_dep = rel_l2(cpu(out['depth']).reshape(-1), cpu(ref['depth']))
+    assert e_img < 1e-4 and e_dep < 1e-4, (e_img, e_dep)
+
+
+def test_uniform_sampler_matches_oracle(dev):
+    import ctypes as C
+    from morpheus_b200 import _lib
+    from oracle import render as orr
+    N, S = 100, 16
+    o, d, g = _rays(N, 4)
+    aabb = torch.tensor([-1.01, -1.01, -1.01, 1.01, 1.01, 1.01])
+    jitter = torch.rand(N, generator=g)
+    ri_o, t0_o, t1_o = orr.sample_uniform(o, d, aabb, S, jitter)
+    ri = torch.empty(N * S, dtype=torch.int64, device=dev)
+    t0 = torch.empty(N * S, device=dev)
+    t1 = torch.empty(N * S, device=dev)
+    od, dd, jd = o.to(dev), d.to(dev), jitter.to(dev)   # keep the device tensors alive across the raw-pointer call
+    _lib.check(_lib.lib().mb_sample_rays_uniform(_lib.ptr(od), _lib.ptr(dd), N, S, (C.c_float * 6)(*aabb.tolist()),
+                                                 _lib.ptr(jd), _lib.ptr(ri), _lib.ptr(t0), _lib.ptr(t1), _lib.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(ri.cpu(), ri_o)
+    np.testing.assert_allclose(cpu(t0), t0_o.numpy(), rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(cpu(t1), t1_o.numpy(), rtol=2e-6, atol=1e-6)
+
+
+def test_adam_vs_torch(dev):
+    import ctypes as C
+    from morpheus_b200 import _lib
+    n = 10000
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(n, generator=g)
+    grads = [torch.randn(n, generator=g) * (10 ** float(torch.randn(1, generator=g))) for _ in range(5)]
+    pt = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pt], lr=5e-4, betas=(0.9, 0.99), eps=1e-15)
+    p = p0.clone().to(dev)
+    m = torch.zeros(n, device=dev)
+    v = torch.zeros(n, device=dev)
+    gid = torch.zeros(n, dtype=torch.uint8, device=dev)
+    lr = torch.tensor([5e-4], device=dev)
+    for step, gr in enumerate(grads, 1):
+        pt.grad = gr.clone()
+        opt.step()
+        grd = gr.to(dev)
+        _lib.check(_lib.lib().mb_adam_step(_lib.ptr(p), _lib.ptr(grd), _lib.ptr(m), _lib.ptr(v), _lib.ptr(gid), _lib.ptr(lr),
+                                           C.c_uint64(n), C.c_float(0.9), C.c_float(0.99), C.c_float(1e-15), step, _lib.stream()))
+    np.testing.assert_allclose(cpu(p), pt.detach().numpy(), rtol=1e-5, atol=1e-7)
