@@ -70,6 +70,12 @@ class ClockSampler:
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons, 'samples': len(sm)}
 
 
+def cpu_threads():
+    """host threads for the CPU arm: all cores up to 32 (beyond that the oracle's many small torch ops get SLOWER from
+    oversubscription: measured 1.2 rays/s at 128 threads vs ~20 rays/s at 8 on the same step)"""
+    return min(os.cpu_count() or 1, 32)
+
+
 def make_state():
     """seeded reference-style initial state (geometric-init SDF ~ sphere of radius 0.4, weight_norm g=|v|, U(-1e-4,1e-4) tables)"""
     torch.manual_seed(2024)   # morpheus.py:45 seed_everything(2024)
@@ -87,7 +93,7 @@ def cpu_step_seconds(state_dict, n_rays, repeats):
     """the ONLY place bench.py executes oracle/: the CPU checker timed as the CPU baseline."""
     from oracle import train_step as ots
     from morpheus_b200.rays import synthetic_real_view_batch
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(cpu_threads())
     params = ots.make_params({k: v.detach().cpu().clone() for k, v in state_dict.items()})
     opt = torch.optim.Adam([v for v in params.values() if v.requires_grad], lr=5e-4, betas=(0.9, 0.99), eps=1e-15)
     times = []
@@ -110,7 +116,7 @@ def run_reference(args, rank):
     times = cpu_step_seconds(m.state_dict(), n_rays, args.warmup + args.steps)[args.warmup:]
     sec = sum(times) / len(times)
     val = n_rays / sec
-    cores = os.cpu_count()
+    cores = cpu_threads()
     line = {'impl': 'reference', 'metric': 'rays_per_sec_train_step', 'value': val, 'unit': 'rays/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': sec * 1e3 * (N_RAYS / n_rays), 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -159,6 +165,7 @@ def main():
     tr = dict(mtrain.DEFAULT_TRAIN_CFG)
     cfg = dict(CONFIG, train=tr)
     R = Renderer(model, OccGridEstimator(torch.tensor([-1.01] * 3 + [1.01] * 3), 128).to(dev), cfg, NUM_FRAMES, uniform_samples=N_SAMPLES)
+    R.world_size = world
     opt = mtrain.FlatAdam(model, tr['lr'])
     n_local = N_RAYS // world
     total_steps = args.warmup + args.steps
@@ -233,15 +240,17 @@ def main():
                     'algorithmic_flops_per_launch': flops_bwd_main,
                     'note': 'fp32 SIMT engine (round 1): its own ceiling is the fp32 FMA pipe (~72 TFLOP/s), see DESIGN.md'}
         launches = sum(v['n'] for v in kern.values()) // args.steps if kern else None
-        times = cpu_step_seconds(state_for_cpu, 64, 1 + args.cpu_baseline_steps)[1:]
-        cpu_val = 64 / (sum(times) / len(times))
+        cpu_val = None
+        if args.cpu_baseline_steps > 0:
+            times = cpu_step_seconds(state_for_cpu, 64, 1 + args.cpu_baseline_steps)[1:]
+            cpu_val = 64 / (sum(times) / len(times))
         line = {'metric': 'rays_per_sec_train_step', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                 'config': workload_config(world), 'clocks': clocks,
                 'e2e': {'value': e2e_val, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
                 'gpu_launches': launches, 'kernels': kern, 'final_loss': last_loss,
                 'roofline': roof,
-                'cpu_baseline': {'value': cpu_val, 'unit': 'rays/s', 'cores': os.cpu_count(), 'kind': 'port',
+                'cpu_baseline': {'value': cpu_val, 'unit': 'rays/s', 'cores': cpu_threads(), 'kind': 'port',
                                  'sample': f'64 rays x {N_SAMPLES} samples (1/64 of the step), fwd+bwd+Adam, {args.cpu_baseline_steps} timed steps after 1 warm-up, oracle port on torch CPU'}}
         print(json.dumps(line))
     if world > 1:

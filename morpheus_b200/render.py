@@ -23,8 +23,10 @@ def get_camera_rays(H, W, fx, fy=None, cx=None, cy=None, device='cuda'):
     return torch.stack([(i + 0.5 - cx) / fx, -(j + 0.5 - cy) / fy, -torch.ones_like(i)], -1)
 
 
-def get_sdf_loss(z_vals, target_d, predicted_sdf, truncation, mask=None):
-    """utils.py:91-113 (including the per-sample normalisation quirk of sum(dim=-1) on [M,1] tensors)."""
+def get_sdf_loss(z_vals, target_d, predicted_sdf, truncation, mask=None, rays_w_depth=None):
+    """utils.py:91-113 (including the per-sample normalisation quirk of sum(dim=-1) on [M,1] tensors).
+    `rays_w_depth` overrides the local count_nonzero(target_d) normaliser: under ray sharding it must be the
+    GLOBAL count (see global_count), otherwise the summed shard gradients differ from the single-GPU gradient."""
     s = predicted_sdf[..., None]
     depth_mask = target_d > 0.
     front_mask = (z_vals < (target_d - truncation)) | ((target_d < 0.) & (z_vals < 3.5))
@@ -33,11 +35,23 @@ def get_sdf_loss(z_vals, target_d, predicted_sdf, truncation, mask=None):
     if mask is not None:
         sdf_mask = sdf_mask & (mask > 0.5)
     n = front_mask.sum(dim=-1) + sdf_mask.sum(dim=-1) + 1e-8
-    rays_w_depth = torch.count_nonzero(target_d)
+    if rays_w_depth is None:
+        rays_w_depth = torch.count_nonzero(target_d)
     fs = torch.max(torch.exp(-5. * s) - 1., s - bound).clamp(min=0.) * front_mask
     fs_loss = (fs.sum(dim=-1) / n).sum() / rays_w_depth
     sdf_loss = ((torch.abs(s - bound) * sdf_mask).sum(dim=-1) / n).sum() / rays_w_depth
     return fs_loss, sdf_loss
+
+
+def global_count(local_count, world_size):
+    """mean-over-ranks of a per-shard count: dividing a shard's SUM by it and the loss by world_size (train_step) yields
+    sum / GLOBAL count after the gradient all-reduce.  One extra 4-byte all-reduce per step."""
+    c = local_count.to(torch.float32).reshape(1)
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        c = c / world_size
+    return c[0]
 
 
 class Renderer:
@@ -50,6 +64,7 @@ class Renderer:
         # BASELINE cfg-1/2/4 use a fixed number of samples per ray (synthetic stand-in): when set, the
         # occupancy-grid march is replaced by the fixed-S lattice over the AABB chord (csrc/sampler.cu:uniform_kernel)
         self.uniform_samples = uniform_samples
+        self.world_size = 1   # set by the data-parallel driver (bench.py / train.py)
 
     @torch.no_grad()
     def sample_uniform(self, rays_o, rays_d, S, jitter=None):
@@ -149,6 +164,7 @@ class Renderer:
             if rays_depth is not None:
                 t_gt = rays_depth[ray_indices]
                 t_mask = rays_mask[ray_indices] if rays_mask is not None else None
-                fs_loss, sdf_loss = get_sdf_loss(t_positions, t_gt, sdf, tr['trunc'], mask=t_mask)
+                cnt = global_count(torch.count_nonzero(t_gt), self.world_size) if self.world_size > 1 else None
+                fs_loss, sdf_loss = get_sdf_loss(t_positions, t_gt, sdf, tr['trunc'], mask=t_mask, rays_w_depth=cnt)
                 results['sdf_loss'], results['fs_loss'] = sdf_loss, fs_loss
         return results
