@@ -141,6 +141,14 @@ typedef struct mb_field_io {
 
 int mb_field_forward(const mb_field_params* p, const mb_field_io* io, mb_stream_t stream);
 
+/* Tensor-core engine (tcgen05 / TMEM): same contract as mb_field_forward.  `tc_weights` is produced by mb_pack_tc from
+ * the fp32 arena: per layer, fp16 (hi, lo) K=16 slabs in the UMMA canonical shared-memory byte order;
+ * layer_desc: n_layers x 8 u32 {w_off, K, K_pad, N_pad, kind, dst_off, K_tc, 0}; tc_off: n_layers x 3 u32
+ * {dst_off, K_tc/16, N_pad} (both tables device-resident, built by morpheus_b200.packing.tc_tables). */
+int mb_pack_tc(const float* arena, const uint32_t* layer_desc, int n_layers, void* out, mb_stream_t stream);
+int mb_field_forward_tc(const mb_field_params* p, const mb_field_io* io, const void* tc_weights, const uint32_t* tc_off,
+                        mb_stream_t stream);
+
 typedef struct mb_field_grads {
     /* upstream (NULL = zero) */
     const float* g_sdf; const float* g_sigma; const float* g_color; const float* g_normal; const float* g_normal_raw; const float* g_deform; const float* g_topo;

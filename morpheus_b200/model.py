@@ -22,6 +22,14 @@ from ._lib import F_COLOR, F_FD, F_FD_WARPED, F_MAIN, F_TOPO_IN, F_WARP, SHADE, 
 from .gridencoder import GridEncoder
 
 PROFILE = _lib.PROFILE
+_TC_TABLES = {}
+
+
+def _tc_tables(dev):
+    key = str(dev)
+    if key not in _TC_TABLES:
+        _TC_TABLES[key] = packing.tc_tables(dev)
+    return _TC_TABLES[key]
 
 
 def safe_normalize(x, eps=1e-20):
@@ -235,8 +243,16 @@ class _FieldQuery(torch.autograd.Function):
         deform, topo = out(3, flags & F_WARP), out(2, flags & F_WARP)
         io.sdf, io.sigma, io.color, io.normal, io.normal_raw = ptr(sdf), ptr(sigma), ptr(color), ptr(normal), ptr(normal_raw)
         io.deform, io.topo = ptr(deform), ptr(topo)
-        with _lib.timed('field_fwd_main' if flags & F_MAIN else 'field_fwd_aux'):
-            check(_lib.lib().mb_field_forward(_lib.C.byref(P), _lib.C.byref(io), stream()), 'field_forward')
+        if _lib.USE_TC:
+            tabs = _tc_tables(dev)
+            tcw = torch.empty(tabs[2], dtype=torch.uint8, device=dev)
+            with _lib.timed('pack_tc'):
+                check(_lib.lib().mb_pack_tc(ptr(arena.detach()), ptr(tabs[0]), 18, ptr(tcw), stream()), 'pack_tc')
+            with _lib.timed('field_fwd_main' if flags & F_MAIN else 'field_fwd_aux'):
+                check(_lib.lib().mb_field_forward_tc(_lib.C.byref(P), _lib.C.byref(io), ptr(tcw), ptr(tabs[1]), stream()), 'field_forward_tc')
+        else:
+            with _lib.timed('field_fwd_main' if flags & F_MAIN else 'field_fwd_aux'):
+                check(_lib.lib().mb_field_forward(_lib.C.byref(P), _lib.C.byref(io), stream()), 'field_forward')
         ctx.cfg = cfg
         ctx.shapes = (code0.shape, code1.shape, code2.shape)
         ctx.save_for_backward(x, t, light, topo_in, arena, emb_sdf, emb_col, codes[0], codes[1], codes[2], beta_d, deform, topo, normal_raw)

@@ -66,3 +66,17 @@ def fill_descs(params):
             d = arr[i]
             d.wt_off, d.w_off, d.b_off, d.K, d.N, d.K_pad, d.N_pad = row
     return params
+
+
+def tc_tables(device):
+    """Static tables for the tensor-core engine: (pack descriptors [18,8] i32, slab offsets [18,3] i32, total bytes).
+    Layer order deform[6], topo[6], sdf[3], color[3]; first layers use the core-aligned K order of csrc/field_fwd_tc.cu."""
+    desc, off, dst = [], [], 0
+    for net in NET_ORDER:
+        for li, (wt_off, w_off, b_off, K, N, Kp, Np) in enumerate(LAYOUT[net]):
+            kind = 1 if (net in ('deform', 'topo') and li == 0) else (2 if (net == 'sdf' and li == 0) else 0)
+            k_tc = 96 if kind == 1 else (80 if kind == 2 else Kp)
+            desc.append([w_off, K, Kp, Np, kind, dst, k_tc, 0])
+            off.append([dst, k_tc // 16, Np])
+            dst += (k_tc // 16) * 64 * Np
+    return (torch.tensor(desc, dtype=torch.int32, device=device), torch.tensor(off, dtype=torch.int32, device=device), dst)

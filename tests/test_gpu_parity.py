@@ -401,3 +401,36 @@ def test_adam_vs_torch(dev):
         _lib.check(_lib.lib().mb_adam_step(_lib.ptr(p), _lib.ptr(grd), _lib.ptr(m), _lib.ptr(v), _lib.ptr(gid), _lib.ptr(lr),
                                            C.c_uint64(n), C.c_float(0.9), C.c_float(0.99), C.c_float(1e-15), step, _lib.stream()))
     np.testing.assert_allclose(cpu(p), pt.detach().numpy(), rtol=1e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05) forward engine vs the fp32 SIMT engine, same inputs, both on the GPU
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('M', [128, 1000 + 37])
+def test_tc_forward_matches_simt(dev, M):
+    from morpheus_b200 import _lib
+    from oracle.fields import init_reference_like_state
+    sd = init_reference_like_state(200, seed=9, randomize=True, emb_scale=0.3)
+    m = make_model(sd, 0.9, dev).eval()
+    g = torch.Generator().manual_seed(5)
+    x = ((torch.rand(M, 3, generator=g) * 2 - 1) * 0.95).to(dev)
+    t = torch.full((M, 1), 77.0 / 200, device=dev)
+    light = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1).to(dev)
+    outs = {}
+    old = _lib.USE_TC
+    try:
+        for tc in (False, True):
+            _lib.USE_TC = tc
+            with torch.no_grad():
+                a = m(x, t, light, ratio=0.4, shading='lambertian')
+                b = m.warp(x, t)
+                c = m.density(x, None)
+            torch.cuda.synchronize()
+            outs[tc] = [a[0], a[1], a[2], a[3], a[4], a[5], b[0], b[1], c['sdf'], c['albedo']]
+    finally:
+        _lib.USE_TC = old
+    names = ['sdf', 'sigma', 'color', 'normal', 'deform', 'normal_raw', 'warp.deform', 'warp.topo', 'cano.sdf', 'cano.albedo']
+    errs = {n: rel_l2(cpu(b), cpu(a)) for n, a, b in zip(names, outs[False], outs[True])}
+    tol = {'normal': 2e-3, 'normal_raw': 2e-3, 'color': 2e-3, 'sigma': 1e-4}
+    bad = {n: e for n, e in errs.items() if e > tol.get(n, 2e-5)}
+    assert not bad, f'{bad}\nall: {errs}'
