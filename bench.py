@@ -142,6 +142,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-baseline-steps', type=int, default=2)
+    ap.add_argument('--no-graph', action='store_true', help='run the step eagerly instead of replaying the captured CUDA graph')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3 if args.impl == 'ours' else 1)
     rank = int(os.environ.get('RANK', '0'))
@@ -185,13 +186,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    graphed = None if args.no_graph else mtrain.GraphedStep(R, opt, to_dev(host[0]), tr, world)
+
+    def one_step(b):
+        if graphed is not None:
+            return graphed.step(b)
+        return mtrain.train_step(R, opt, b if b['rays_o'].is_cuda else to_dev(b), tr, world)
+
     def run(e2e, profile):
+        """K timed steps.  e2e=False: batches already resident in HBM (value); e2e=True: every step copies its batch from
+        pinned host memory and reads the loss back (what a user of train_step pays)."""
         resident = [to_dev(b) for b in host] if not e2e else None
         torch.cuda.synchronize()
         loss_host = torch.zeros(1).pin_memory()
         for s in range(args.warmup):
-            b = to_dev(host[s]) if e2e else resident[s]
-            loss = mtrain.train_step(R, opt, b, tr, world)
+            loss = one_step(host[s] if e2e else resident[s])
         barrier()
         sampler = ClockSampler(local_rank) if rank == 0 else None
         if sampler:
@@ -202,8 +211,7 @@ def main():
         e0.record()
         for s in range(args.warmup, total_steps):
             flush.fill_(s & 0xFF)
-            b = to_dev(host[s]) if e2e else resident[s]
-            loss = mtrain.train_step(R, opt, b, tr, world)
+            loss = one_step(host[s] if e2e else resident[s])
             if e2e:
                 loss_host.copy_(loss.reshape(1), non_blocking=True)
                 torch.cuda.current_stream().synchronize()   # the user reads the loss every step (morpheus.py:1426 loss.item())
@@ -217,11 +225,27 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), clocks, float(loss)
 
+    def kernel_pass():
+        """per-kernel CUDA-event timing of OUR launches: the same steps run eagerly (events cannot be read back from a
+        replayed graph), on the launching stream, after warm-up"""
+        resident = [to_dev(b) for b in host[:args.warmup + min(args.steps, 5)]]
+        for b in resident[:args.warmup]:
+            mtrain.train_step(R, opt, b, tr, world)
+        torch.cuda.synchronize()
+        prof.enabled = True
+        prof.reset()
+        for b in resident[args.warmup:]:
+            flush.fill_(1)
+            mtrain.train_step(R, opt, b, tr, world)
+        out = prof.summary()
+        prof.enabled = False
+        return out, len(resident) - args.warmup
+
     from morpheus_b200 import model as mmodel
     prof = mmodel.PROFILE
-    ms_total, clocks, last_loss = run(e2e=False, profile=True)
-    kern = prof.summary()
+    ms_total, clocks, last_loss = run(e2e=False, profile=False)
     ms_e2e, _, _ = run(e2e=True, profile=False)
+    kern, kern_steps = kernel_pass()
     if rank == 0:
         ms_step = ms_total / args.steps
         value = N_RAYS / (ms_step * 1e-3)
@@ -239,14 +263,14 @@ def main():
                     'traffic': None, 'peak_source': which, 'avg_launch_ms': k['avg_ms'], 'launches_timed': k['n'],
                     'algorithmic_flops_per_launch': flops_bwd_main,
                     'note': 'fp32 SIMT engine (round 1): its own ceiling is the fp32 FMA pipe (~72 TFLOP/s), see DESIGN.md'}
-        launches = sum(v['n'] for v in kern.values()) // args.steps if kern else None
+        launches = sum(v['n'] for v in kern.values()) // max(kern_steps, 1) if kern else None
         cpu_val = None
         if args.cpu_baseline_steps > 0:
             times = cpu_step_seconds(state_for_cpu, 64, 1 + args.cpu_baseline_steps)[1:]
             cpu_val = 64 / (sum(times) / len(times))
         line = {'metric': 'rays_per_sec_train_step', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': workload_config(world), 'clocks': clocks,
+                'config': dict(workload_config(world), cuda_graph=(not args.no_graph)), 'clocks': clocks,
                 'e2e': {'value': e2e_val, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
                 'gpu_launches': launches, 'kernels': kern, 'final_loss': last_loss,
                 'roofline': roof,

@@ -173,6 +173,9 @@ int mb_occ_binarize(const float* occs, uint32_t n, float thre, uint8_t* binaries
  * models/model.py:313-324); bias-corrected torch.optim.Adam semantics, no weight decay. */
 int mb_adam_step(float* p, const float* g, float* m, float* v, const uint8_t* group_id, const float* group_lr,
                  uint64_t n, float beta1, float beta2, float eps, int step, mb_stream_t stream);
+/* same, with the (1-based) step count read from device memory so the launch can be replayed inside a CUDA graph */
+int mb_adam_step_dev(float* p, const float* g, float* m, float* v, const uint8_t* group_id, const float* group_lr,
+                     uint64_t n, float beta1, float beta2, float eps, const int32_t* step_dev, mb_stream_t stream);
 
 /* ---- (7) SDS scalar chain: grad = grad_scale*(1-abar_t)*(eps_u + s*(eps_c-eps_u) - eps), nan_to_num --- */
 int mb_sds_grad(const float* eps_uncond, const float* eps_cond, const float* noise, float guidance_scale,

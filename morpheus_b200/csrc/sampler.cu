@@ -112,7 +112,12 @@ __global__ void occ_binarize_kernel(const float* __restrict__ occs, uint32_t n, 
 // ---- fused Adam (torch.optim.Adam semantics: bias-corrected, eps added after sqrt(v_hat)) -----------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             const uint8_t* __restrict__ gid, const float* __restrict__ glr, uint64_t n, float b1, float b2,
-                            float eps, float bc1, float bc2_sqrt) {
+                            float eps, float bc1, float bc2_sqrt, const int32_t* __restrict__ step_dev) {
+    if (step_dev) {   // device-resident step count: the launch is then replayable inside a CUDA graph
+        const float t = (float)__ldg(step_dev);
+        bc1 = 1.0f - powf(b1, t);
+        bc2_sqrt = sqrtf(1.0f - powf(b2, t));
+    }
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const float gi = g[i];
         const float mi = m[i] + (1.0f - b1) * (gi - m[i]);            // lerp form used by torch
@@ -203,8 +208,19 @@ extern "C" int mb_adam_step(float* p, const float* g, float* m, float* v, const 
     int sms = mb_sm_count();
     uint64_t blocks = (n + 255) / 256;
     if (blocks > (uint64_t)sms * 8) blocks = (uint64_t)sms * 8;
-    adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, group_id, group_lr, n, beta1, beta2, eps, bc1, bc2_sqrt);
+    adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, group_id, group_lr, n, beta1, beta2, eps, bc1, bc2_sqrt, nullptr);
     return check_launch("adam_step");
+}
+
+extern "C" int mb_adam_step_dev(float* p, const float* g, float* m, float* v, const uint8_t* group_id, const float* group_lr, uint64_t n,
+                                float beta1, float beta2, float eps, const int32_t* step_dev, mb_stream_t stream) {
+    if (n == 0) return MB_OK;
+    if (!p || !g || !m || !v || !group_lr || !step_dev) { set_error("adam_step_dev: bad argument"); return MB_EINVAL; }
+    int sms = mb_sm_count();
+    uint64_t blocks = (n + 255) / 256;
+    if (blocks > (uint64_t)sms * 8) blocks = (uint64_t)sms * 8;
+    adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, group_id, group_lr, n, beta1, beta2, eps, 1.f, 1.f, step_dev);
+    return check_launch("adam_step_dev");
 }
 
 extern "C" int mb_sds_grad(const float* eps_uncond, const float* eps_cond, const float* noise, float guidance_scale,

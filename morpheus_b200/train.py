@@ -74,6 +74,7 @@ class FlatAdam:
         self.group_names = [g['name'] for g in groups]
         self.group_lr = torch.tensor(lrs, device=dev, dtype=torch.float32)
         self.betas, self.eps, self.t, self.n = betas, eps, 0, n
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # device-side step count (CUDA-graph replayable)
         self.params = plist
 
     def set_group_lr(self, name, lr):
@@ -88,10 +89,11 @@ class FlatAdam:
 
     def step(self):
         self.t += 1
+        self.step_dev += 1
         with _lib.timed('adam'):
-          check(_lib.lib().mb_adam_step(ptr(self.flat), ptr(self.grad), ptr(self.m), ptr(self.v), ptr(self.group_id), ptr(self.group_lr),
-                                      C.c_uint64(self.n), C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
-                                      self.t, stream()), 'adam_step')
+            check(_lib.lib().mb_adam_step_dev(ptr(self.flat), ptr(self.grad), ptr(self.m), ptr(self.v), ptr(self.group_id), ptr(self.group_lr),
+                                              C.c_uint64(self.n), C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
+                                              ptr(self.step_dev), stream()), 'adam_step')
 
 
 def train_step(renderer, opt, batch, tr, world_size=1, shading='albedo_normal', samples=None):
@@ -109,3 +111,34 @@ def train_step(renderer, opt, batch, tr, world_size=1, shading='albedo_normal', 
     opt.step()
     model.invalidate()
     return loss.detach()
+
+
+class GraphedStep:
+    """The whole optimiser step (render forward, losses, backward, all-reduce, Adam) captured ONCE as a CUDA graph and
+    replayed per iteration: the ~1000 small launches of the host-side glue (parameter packing, indexing, loss heads)
+    cost no CPU time any more.  Inputs live in static device buffers (`self.batch`); shapes are fixed (fixed-S sampler),
+    RNG draws inside the step use torch's graph-safe Philox offsets, the Adam step count is device-resident."""
+
+    def __init__(self, renderer, opt, example_batch, tr, world_size=1, warmup=3):
+        self.renderer, self.opt, self.tr, self.world = renderer, opt, tr, world_size
+        self.batch = {k: v.clone() for k, v in example_batch.items()}
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                train_step(renderer, opt, self.batch, tr, world_size)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = train_step(renderer, opt, self.batch, tr, world_size)
+
+    def load(self, batch, non_blocking=True):
+        for k, v in batch.items():
+            self.batch[k].copy_(v, non_blocking=non_blocking)
+
+    def step(self, batch=None):
+        if batch is not None:
+            self.load(batch)
+        self.graph.replay()
+        return self.loss

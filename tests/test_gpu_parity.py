@@ -394,12 +394,18 @@ def test_adam_vs_torch(dev):
     v = torch.zeros(n, device=dev)
     gid = torch.zeros(n, dtype=torch.uint8, device=dev)
     lr = torch.tensor([5e-4], device=dev)
+    step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
     for step, gr in enumerate(grads, 1):
         pt.grad = gr.clone()
         opt.step()
         grd = gr.to(dev)
-        _lib.check(_lib.lib().mb_adam_step(_lib.ptr(p), _lib.ptr(grd), _lib.ptr(m), _lib.ptr(v), _lib.ptr(gid), _lib.ptr(lr),
-                                           C.c_uint64(n), C.c_float(0.9), C.c_float(0.99), C.c_float(1e-15), step, _lib.stream()))
+        if step % 2:
+            _lib.check(_lib.lib().mb_adam_step(_lib.ptr(p), _lib.ptr(grd), _lib.ptr(m), _lib.ptr(v), _lib.ptr(gid), _lib.ptr(lr),
+                                               C.c_uint64(n), C.c_float(0.9), C.c_float(0.99), C.c_float(1e-15), step, _lib.stream()))
+        else:   # device-resident step count variant (CUDA-graph replayable)
+            step_dev.fill_(step)
+            _lib.check(_lib.lib().mb_adam_step_dev(_lib.ptr(p), _lib.ptr(grd), _lib.ptr(m), _lib.ptr(v), _lib.ptr(gid), _lib.ptr(lr),
+                                                   C.c_uint64(n), C.c_float(0.9), C.c_float(0.99), C.c_float(1e-15), _lib.ptr(step_dev), _lib.stream()))
     np.testing.assert_allclose(cpu(p), pt.detach().numpy(), rtol=1e-5, atol=1e-7)
 
 
