@@ -98,6 +98,8 @@ int mb_composite_backward(const int32_t* seg, uint32_t N, uint32_t M, const floa
 #define MB_F_FD 8u            /* 6-point finite-difference normal                   model.py:367-398 */
 #define MB_F_FD_WARPED 16u    /* ... evaluated at x+deform instead of x             model.py:391-395 */
 #define MB_F_TOPO_IN 32u      /* take topo from topo_in instead of zeros / warp */
+#define MB_F_SKIP_WARP_BWD 64u /* backward only: do not back-propagate the deform/topology nets; write d/d(deform), d/d(topo)
+                                 to g_def_out / g_topo_out instead (consumed by mb_field_backward_warp_tc) */
 #define MB_SHADE_ALBEDO 0
 #define MB_SHADE_LAMBERTIAN 1   /* albedo*(ratio+(1-ratio)*max(n.l,0)); 'albedo_normal' is ratio=1 */
 #define MB_SHADE_TEXTURELESS 2
@@ -146,8 +148,10 @@ int mb_field_forward(const mb_field_params* p, const mb_field_io* io, mb_stream_
  * layer_desc: n_layers x 8 u32 {w_off, K, K_pad, N_pad, kind, dst_off, K_tc, 0}; tc_off: n_layers x 3 u32
  * {dst_off, K_tc/16, N_pad} (both tables device-resident, built by morpheus_b200.packing.tc_tables). */
 int mb_pack_tc(const float* arena, const uint32_t* layer_desc, int n_layers, void* out, mb_stream_t stream);
+/* stash (nullable): [ceil(M/128)][10][65536] bytes; with WARP the hidden activations of the deform / topology nets are
+ * stored there (fp16 hi/lo operand tiles) for mb_field_backward_warp_tc */
 int mb_field_forward_tc(const mb_field_params* p, const mb_field_io* io, const void* tc_weights, const uint32_t* tc_off,
-                        mb_stream_t stream);
+                        void* stash, mb_stream_t stream);
 
 typedef struct mb_field_grads {
     /* upstream (NULL = zero) */
@@ -159,9 +163,19 @@ typedef struct mb_field_grads {
     /* written: */
     float* g_x;                     /* [M,3] or NULL */
     float* g_topo_in;               /* [M,2] or NULL */
+    float* g_def_out;               /* [M,3], with MB_F_SKIP_WARP_BWD */
+    float* g_topo_out;              /* [M,2], with MB_F_SKIP_WARP_BWD */
 } mb_field_grads;
 
 int mb_field_backward(const mb_field_params* p, const mb_field_io* io, const mb_field_grads* g, mb_stream_t stream);
+
+/* Tensor-core backward of the deformation + topology networks (12 dense layers): consumes the activation stash of
+ * mb_field_forward_tc, d/d(deform) [M,3] and d/d(topo) [M,2] (from mb_field_backward with MB_F_SKIP_WARP_BWD) and
+ * accumulates weight/bias gradients into g_arena, code-line gradients into g_code, and ADDS d/dx into g_x [M,3].
+ * tc_weights_t / tc_off_t: dgrad operands packed by mb_pack_tc in mode 1 (12 layers: deform[6], topo[6]). */
+int mb_field_backward_warp_tc(const mb_field_params* p, const float* x, const float* t, uint32_t M, const float* g_def,
+                              const float* g_topo, const void* stash, const void* tc_weights_t, const uint32_t* tc_off_t,
+                              float* g_arena, float* const g_code[3], float* g_x, mb_stream_t stream);
 
 /* ---- (5) occupancy refresh: occs = max(decay*occs, sigma*step) on selected cells ---------------- */
 int mb_occ_update(float* occs, const int64_t* cell_idx, const float* sigma, uint32_t n, float decay, float step,

@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(_HERE, 'libmorpheus_b200.so')
 _lib = None
 # tensor-core (tcgen05) forward engine; MORPHEUS_B200_TC=0 selects the fp32 SIMT engine (kept as the parity reference)
 USE_TC = os.environ.get('MORPHEUS_B200_TC', '1') != '0'
+# tensor-core backward of the deform/topology nets (needs the forward activation stash, i.e. USE_TC)
+USE_TC_BWD = os.environ.get('MORPHEUS_B200_TC_BWD', '1') != '0'
 
 
 class LayerDesc(C.Structure):
@@ -44,17 +46,17 @@ class FieldGrads(C.Structure):
                 ('g_deform', C.c_void_p), ('g_topo', C.c_void_p),
                 ('deform', C.c_void_p), ('topo', C.c_void_p), ('normal_raw', C.c_void_p),
                 ('g_arena', C.c_void_p), ('g_emb_sdf', C.c_void_p), ('g_emb_col', C.c_void_p), ('g_code', C.c_void_p * 3),
-                ('g_beta', C.c_void_p), ('g_x', C.c_void_p), ('g_topo_in', C.c_void_p)]
+                ('g_beta', C.c_void_p), ('g_x', C.c_void_p), ('g_topo_in', C.c_void_p), ('g_def_out', C.c_void_p), ('g_topo_out', C.c_void_p)]
 
 
-F_WARP, F_MAIN, F_COLOR, F_FD, F_FD_WARPED, F_TOPO_IN = 1, 2, 4, 8, 16, 32
+F_WARP, F_MAIN, F_COLOR, F_FD, F_FD_WARPED, F_TOPO_IN, F_SKIP_WARP_BWD = 1, 2, 4, 8, 16, 32, 64
 SHADE = {'albedo': 0, 'lambertian': 1, 'albedo_normal': 1, 'textureless': 2, 'normal': 3}
 
 # every symbol include/morpheus_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ['mb_version', 'mb_last_error', 'mb_sm_count', 'mb_grid_encode_forward', 'mb_grid_encode_backward',
            'mb_sample_rays_count', 'mb_sample_rays_write', 'mb_sample_rays_uniform', 'mb_composite_forward',
            'mb_composite_backward', 'mb_field_forward', 'mb_field_backward', 'mb_occ_update', 'mb_occ_binarize',
-           'mb_adam_step', 'mb_sds_grad', 'mb_add_noise', 'mb_pack_tc', 'mb_field_forward_tc', 'mb_adam_step_dev']
+           'mb_adam_step', 'mb_sds_grad', 'mb_add_noise', 'mb_pack_tc', 'mb_field_forward_tc', 'mb_adam_step_dev', 'mb_field_backward_warp_tc']
 
 
 def lib():

@@ -360,7 +360,21 @@ __global__ void __launch_bounds__(FT, 1) field_bwd_kernel(const mb_field_params 
         }
 
         // ---- deformation / topology networks ----
-        if (flags & MB_F_WARP) {
+        if ((flags & MB_F_WARP) && (flags & MB_F_SKIP_WARP_BWD)) {
+            // hand d/d(deform), d/d(topo) to the tensor-core backward of the two big networks
+            for (int idx = tid; idx < 3 * TM; idx += FT) {
+                const int m = idx / 3, a = idx - m * 3;
+                if (m < nv) {
+                    float v = gxw[a * P + m];
+                    if (gr.g_deform) v += gr.g_deform[(size_t)m0 * 3 + idx];
+                    gr.g_def_out[(size_t)m0 * 3 + idx] = v;
+                }
+            }
+            for (int idx = tid; idx < 2 * TM; idx += FT) {
+                const int m = idx / 2, a = idx - m * 2;
+                if (m < nv) gr.g_topo_out[(size_t)m0 * 2 + idx] = gtopo[a * P + m];
+            }
+        } else if (flags & MB_F_WARP) {
             build_freq<TM, P>(sx, in0, (int)p.n_freq);
             build_code_b<TM, P>(p, st, in0 + 39 * P);
             zero_rows_b<TM, P>(in0, 87, 96);
@@ -469,6 +483,7 @@ extern "C" int mb_field_backward(const mb_field_params* p, const mb_field_io* io
     if (!p || !io || !g) { set_error("field_backward: null argument"); return MB_EINVAL; }
     if (io->M == 0) return MB_OK;
     if (!io->x || !p->arena || !g->g_arena) { set_error("field_backward: x/arena/g_arena is null"); return MB_EINVAL; }
+    if ((io->flags & MB_F_SKIP_WARP_BWD) && (!g->g_def_out || !g->g_topo_out)) { set_error("field_backward: SKIP_WARP_BWD needs g_def_out/g_topo_out"); return MB_EINVAL; }
     if ((io->flags & MB_F_WARP) && (!io->t || !g->deform || !g->topo || !g->g_code[0] || !g->g_code[1] || !g->g_code[2])) {
         set_error("field_backward: WARP needs t, saved deform/topo and g_code");
         return MB_EINVAL;

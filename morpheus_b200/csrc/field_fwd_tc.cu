@@ -14,6 +14,7 @@
 //     bulk copies and the MMAs; hand-offs are mbarriers (a_ready: 256 arrivals, acc_ready / empty[]: tcgen05.commit).
 #include "field_common.cuh"
 #include "tc_common.cuh"
+#include "tc_field.cuh"
 
 namespace mb {
 namespace tc {
@@ -23,7 +24,6 @@ constexpr int NWORK = 256;              // worker threads (8 warps)
 constexpr int NTHREADS = NWORK + 32;    // + control warp
 constexpr int NSTAGE = 4;
 constexpr int STAGE_BYTES = 8192;       // one K=16 slab of a 128-wide layer: (hi + lo) * 2 cores * 128 rows * 16 B
-constexpr int A_LO_OFF = 32768;         // A_lo tile offset (bytes) from A_hi
 constexpr int MAX_OPS = 40;
 
 struct Op { uint32_t src_off; uint16_t nk, n, n_pad, pad; };   // src_off: bytes into the tc weight arena
@@ -47,69 +47,6 @@ struct Smem {
     static constexpr int TOTAL = TMEMH + 16;
 };
 static_assert(Smem::OPS % 4 == 0 && Smem::BAR % 8 == 0, "alignment");
-
-__device__ __forceinline__ void store_core(uint8_t* A, int m, int kc, const float (&v)[8]) {
-    uint4 hi, lo;
-    split8(v, hi, lo);
-    uint8_t* p = A + kc * 2048 + (m >> 3) * 128 + (m & 7) * 16;
-    *reinterpret_cast<uint4*>(p) = hi;
-    *reinterpret_cast<uint4*>(p + A_LO_OFF) = lo;
-}
-
-// freq encoding in the tc feature order: cores 0..4 = [p(3), sin/cos bands (36), 0]
-__device__ __forceinline__ void build_freq_tc(uint8_t* A, int m, const float p[3], int n_freq) {
-    float f[40];
-    f[0] = p[0]; f[1] = p[1]; f[2] = p[2];
-    float fr = 1.0f;
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            float s = 0.f, c = 0.f;
-            if (k < n_freq) sincosf(p[a] * fr, &s, &c);
-            f[3 + 6 * k + a] = s;
-            f[6 + 6 * k + a] = c;
-        }
-        fr *= 2.0f;
-    }
-    f[39] = 0.f;
-#pragma unroll
-    for (int c = 0; c < 5; c++) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = f[c * 8 + i];
-        store_core(A, m, c, v);
-    }
-}
-
-// 4 grid levels (8 features) -> one core
-__device__ __forceinline__ void build_grid_core_tc(uint8_t* A, int m, int kc, const GridCtx& g, int level0, const float p[3]) {
-    float u[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) u[d] = __fdiv_rn(__fadd_rn(p[d], g.bound), g.two_bound);
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        float feat[2] = {0.f, 0.f};
-        if ((uint32_t)(level0 + j) < g.n_levels) grid_eval(g, level0 + j, u, feat, nullptr);
-        v[2 * j] = feat[0];
-        v[2 * j + 1] = feat[1];
-    }
-    store_core(A, m, kc, v);
-}
-
-__device__ __forceinline__ float code_value(const mb_field_params& p, int v, int c, float t) {
-    const int S = (int)p.code_len[v];
-    t = fminf(fmaxf(t, 0.f), 1.f);
-    const float g = __fsub_rn(__fmul_rn(t, 2.f), 1.f);
-    const float pos = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), (float)(S - 1));
-    int i0 = min(max((int)floorf(pos), 0), S - 1);
-    const float w1 = pos - (float)i0, w0 = 1.f - w1;
-    const float* line = p.code[v] + (size_t)c * S;
-    float val = __ldg(line + i0) * w0;
-    if (i0 + 1 <= S - 1) val += __ldg(line + i0 + 1) * w1;
-    return val;
-}
 
 struct Ctx {
     uint8_t* smem;
@@ -152,7 +89,8 @@ __device__ __forceinline__ void epilogue_hidden(Ctx& c, const float* __restrict_
 }
 
 __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_field_params p, const mb_field_io io,
-                                                                  const uint8_t* __restrict__ tcw, const uint32_t* __restrict__ tc_off) {
+                                                                  const uint8_t* __restrict__ tcw, const uint32_t* __restrict__ tc_off,
+                                                                  uint8_t* __restrict__ stash) {
     extern __shared__ __align__(128) uint8_t smem[];
     float* sx = reinterpret_cast<float*>(smem + Smem::SX);
     float* sxw = reinterpret_cast<float*>(smem + Smem::SXW);
@@ -244,6 +182,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
                 mbar_wait(c.a_ready, a_count & 1);
                 a_count++;
                 tc_fence_after();
+                // training: stash the hidden activations A_1..A_5 of the deform / topology nets (the A operand of ops
+                // 1..5 and 7..11 of a tile) for the tensor-core backward: one 64 KB bulk store per layer
+                const uint32_t op_in_tile = (uint32_t)(u_op % n_ops);
+                const bool do_stash = stash && (flags & MB_F_WARP) && op_in_tile < 12 && (op_in_tile % 6) >= 1;
+                if (do_stash) {
+                    const uint64_t tile = blockIdx.x + (u_op / n_ops) * (uint64_t)gridDim.x;
+                    const uint32_t slot = (op_in_tile / 6) * 5 + (op_in_tile % 6) - 1;
+                    bulk_s2g(stash + (tile * 10 + slot) * 65536ull, A, 65536);
+                }
                 const uint32_t idesc = make_idesc_f16(o.n);
                 const uint32_t lbo_b = 16u * o.n_pad;
                 for (uint32_t s = 0; s < o.nk; s++) {
@@ -262,6 +209,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
                     uses++;
                     top_up();
                 }
+                if (do_stash) bulk_store_wait_read();     // the epilogue of this op overwrites A
                 umma_commit(c.acc_ready);
             }
         }
@@ -490,24 +438,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
 // K permutation of the first layers (inputs are built core-aligned by the kernel):
 //   deform/topo L0: tc k 0..38 -> k, 39 -> 0-pad, 40..87 -> 39 + (k-40) (code), 88..95 -> pad
 //   sdf L0        : tc k 0..38 -> k, 39 -> pad, 40..71 -> 39 + (k-40) (grid), 72,73 -> 71,72 (topo), 74..79 -> pad
-__device__ __forceinline__ int tc_korig(int kind, int k) {
-    if (kind == 1) { if (k < 39) return k; if (k == 39) return -1; if (k < 88) return 39 + (k - 40); return -1; }
-    if (kind == 2) { if (k < 39) return k; if (k == 39) return -1; if (k < 72) return 39 + (k - 40); if (k < 74) return 71 + (k - 72); return -1; }
-    return k;
-}
-
 __global__ void pack_tc_kernel(const float* __restrict__ arena, const uint32_t* __restrict__ desc /* per layer: w_off, K, K_pad, N_pad, kind, dst_off, K_tc */,
                                int n_layers, uint8_t* __restrict__ out) {
     const int layer = blockIdx.y;
     if (layer >= n_layers) return;
     const uint32_t* d = desc + layer * 8;
-    const uint32_t w_off = d[0], K = d[1], K_pad = d[2], N_pad = d[3], kind = d[4], dst = d[5], K_tc = d[6];
+    // d = {src_off, K_valid, pitch, rows, kind, dst_off, inner, mode}
+    //   mode 0 (forward B operand):  B[r = n][kk = k_tc] = W[n][korig(k_tc)]      src = W  n-major, pitch K_pad
+    //   mode 1 (dgrad   B operand):  B[r = k_tc][kk = n] = Wt[korig(k_tc)][n]     src = Wt k-major, pitch N_pad
+    const uint32_t w_off = d[0], K = d[1], K_pad = d[2], N_pad = d[3], kind = d[4], dst = d[5], K_tc = d[6], mode = d[7];
     const uint32_t total = N_pad * K_tc;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const uint32_t n = i / K_tc, k = i - n * K_tc;
-        const int ko = tc_korig((int)kind, (int)k);
+        const int ko = tc_korig((int)kind, (int)(mode == 0 ? k : n));
         float w = 0.f;
-        if (ko >= 0 && (uint32_t)ko < K) w = arena[w_off + (size_t)n * K_pad + ko];
+        if (ko >= 0 && (uint32_t)ko < K) w = (mode == 0) ? arena[w_off + (size_t)n * K_pad + ko] : arena[w_off + (size_t)ko * K_pad + k];
         const __half h = __float2half_rn(w);
         const __half l = __float2half_rn(w - __half2float(h));
         const uint32_t s = k >> 4, kc = (k >> 3) & 1, ki = k & 7;
@@ -530,7 +475,7 @@ extern "C" int mb_pack_tc(const float* arena, const uint32_t* layer_desc, int n_
 }
 
 extern "C" int mb_field_forward_tc(const mb_field_params* p, const mb_field_io* io, const void* tc_weights, const uint32_t* tc_off,
-                                   mb_stream_t stream) {
+                                   void* stash, mb_stream_t stream) {
     using namespace mb;
     if (!p || !io || !tc_weights || !tc_off) { set_error("field_forward_tc: null argument"); return MB_EINVAL; }
     if (io->M == 0) return MB_OK;
@@ -548,6 +493,6 @@ extern "C" int mb_field_forward_tc(const mb_field_params* p, const mb_field_io* 
     }
     const uint32_t n_tiles = div_up(io->M, tc::TM);
     const uint32_t grid = min(n_tiles, (uint32_t)mb_sm_count() * 2u);
-    tc::field_fwd_tc_kernel<<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(*p, *io, (const uint8_t*)tc_weights, tc_off);
+    tc::field_fwd_tc_kernel<<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(*p, *io, (const uint8_t*)tc_weights, tc_off, (uint8_t*)stash);
     return check_launch("field_forward_tc");
 }

@@ -25,6 +25,16 @@ PROFILE = _lib.PROFILE
 _TC_TABLES = {}
 
 
+_TC_TABLES_T = {}
+
+
+def _tc_tables_dgrad(dev):
+    key = str(dev)
+    if key not in _TC_TABLES_T:
+        _TC_TABLES_T[key] = packing.tc_tables_dgrad(dev)
+    return _TC_TABLES_T[key]
+
+
 def _tc_tables(dev):
     key = str(dev)
     if key not in _TC_TABLES:
@@ -243,17 +253,22 @@ class _FieldQuery(torch.autograd.Function):
         deform, topo = out(3, flags & F_WARP), out(2, flags & F_WARP)
         io.sdf, io.sigma, io.color, io.normal, io.normal_raw = ptr(sdf), ptr(sigma), ptr(color), ptr(normal), ptr(normal_raw)
         io.deform, io.topo = ptr(deform), ptr(topo)
+        stash = None
         if _lib.USE_TC:
             tabs = _tc_tables(dev)
+            needs_grad = any(ctx.needs_input_grad)   # (grad mode itself is off inside Function.forward)
+            if _lib.USE_TC_BWD and (flags & F_WARP) and needs_grad:
+                stash = torch.empty(((M + 127) // 128) * 10 * 65536, dtype=torch.uint8, device=dev)
             tcw = torch.empty(tabs[2], dtype=torch.uint8, device=dev)
             with _lib.timed('pack_tc'):
                 check(_lib.lib().mb_pack_tc(ptr(arena.detach()), ptr(tabs[0]), 18, ptr(tcw), stream()), 'pack_tc')
             with _lib.timed('field_fwd_main' if flags & F_MAIN else 'field_fwd_aux'):
-                check(_lib.lib().mb_field_forward_tc(_lib.C.byref(P), _lib.C.byref(io), ptr(tcw), ptr(tabs[1]), stream()), 'field_forward_tc')
+                check(_lib.lib().mb_field_forward_tc(_lib.C.byref(P), _lib.C.byref(io), ptr(tcw), ptr(tabs[1]), ptr(stash), stream()), 'field_forward_tc')
         else:
             with _lib.timed('field_fwd_main' if flags & F_MAIN else 'field_fwd_aux'):
                 check(_lib.lib().mb_field_forward(_lib.C.byref(P), _lib.C.byref(io), stream()), 'field_forward')
         ctx.cfg = cfg
+        ctx.stash = stash
         ctx.shapes = (code0.shape, code1.shape, code2.shape)
         ctx.save_for_backward(x, t, light, topo_in, arena, emb_sdf, emb_col, codes[0], codes[1], codes[2], beta_d, deform, topo, normal_raw)
         ctx.set_materialize_grads(False)
@@ -294,8 +309,25 @@ class _FieldQuery(torch.autograd.Function):
         G.g_arena, G.g_emb_sdf, G.g_emb_col, G.g_beta, G.g_x, G.g_topo_in = map(ptr, (g_arena, g_es, g_ec, g_beta, g_x, g_topo_in))
         for i in range(3):
             G.g_code[i] = g_codes[i].data_ptr()
+        stash = getattr(ctx, 'stash', None)
+        g_def_out = g_topo_out = None
+        if stash is not None:
+            io.flags = flags | _lib.F_SKIP_WARP_BWD
+            g_def_out = torch.empty(M, 3, device=x.device)
+            g_topo_out = torch.empty(M, 2, device=x.device)
+            G.g_def_out, G.g_topo_out = ptr(g_def_out), ptr(g_topo_out)
         with _lib.timed('field_bwd_main' if flags & F_MAIN else 'field_bwd_aux'):
             check(_lib.lib().mb_field_backward(_lib.C.byref(P), _lib.C.byref(io), _lib.C.byref(G), stream()), 'field_backward')
+        if stash is not None:
+            tabs = _tc_tables_dgrad(x.device)
+            tcw_t = torch.empty(tabs[2], dtype=torch.uint8, device=x.device)
+            check(_lib.lib().mb_pack_tc(ptr(arena.detach()), ptr(tabs[0]), 12, ptr(tcw_t), stream()), 'pack_tc(dgrad)')
+            gcode_ptrs = (_lib.C.c_void_p * 3)(*[g.data_ptr() for g in g_codes])
+            with _lib.timed('field_bwd_warp_tc'):
+                check(_lib.lib().mb_field_backward_warp_tc(_lib.C.byref(P), ptr(x), ptr(t), M, ptr(g_def_out), ptr(g_topo_out), ptr(stash),
+                                                           ptr(tcw_t), ptr(tabs[1]), ptr(g_arena), gcode_ptrs, ptr(g_x), stream()),
+                      'field_backward_warp_tc')
+            ctx.stash = None
         gc = [g.reshape(s) for g, s in zip(g_codes, ctx.shapes)]
         return (None, g_x, None, None, g_topo_in, g_arena, g_es, g_ec, gc[0], gc[1], gc[2], g_beta.reshape(()))
 

@@ -80,3 +80,17 @@ def tc_tables(device):
             off.append([dst, k_tc // 16, Np])
             dst += (k_tc // 16) * 64 * Np
     return (torch.tensor(desc, dtype=torch.int32, device=device), torch.tensor(off, dtype=torch.int32, device=device), dst)
+
+
+def tc_tables_dgrad(device):
+    """Tables for the tensor-core backward of the deform / topology nets: dgrad B operands B[k_tc][n] = Wt[korig(k_tc)][n]
+    (pack mode 1).  -> (pack descriptors [12,8], slab table [12,3] = {offset, N_pad/16, rows}, total bytes)"""
+    desc, off, dst = [], [], 0
+    for net in ('deform', 'topo'):
+        for li, (wt_off, w_off, b_off, K, N, Kp, Np) in enumerate(LAYOUT[net]):
+            kind = 1 if li == 0 else 0
+            rows = 96 if kind == 1 else Kp
+            desc.append([wt_off, K, Np, rows, kind, dst, Np, 1])
+            off.append([dst, Np // 16, rows])
+            dst += (Np // 16) * 64 * rows
+    return (torch.tensor(desc, dtype=torch.int32, device=device), torch.tensor(off, dtype=torch.int32, device=device), dst)

@@ -440,3 +440,39 @@ def test_tc_forward_matches_simt(dev, M):
     tol = {'normal': 2e-3, 'normal_raw': 2e-3, 'color': 2e-3, 'sigma': 1e-4}
     bad = {n: e for n, e in errs.items() if e > tol.get(n, 2e-5)}
     assert not bad, f'{bad}\nall: {errs}'
+
+
+def test_tc_backward_matches_simt(dev):
+    """tensor-core backward of the deform/topology nets (stash + wgrad/dgrad on tcgen05) vs the fp32 SIMT backward"""
+    from morpheus_b200 import _lib
+    from oracle.fields import init_reference_like_state
+    sd = init_reference_like_state(200, seed=13, randomize=True, emb_scale=0.3)
+    M = 700
+    g = torch.Generator().manual_seed(8)
+    x = ((torch.rand(M, 3, generator=g) * 2 - 1) * 0.95).to(dev)
+    t = torch.full((M, 1), 113.0 / 200, device=dev)
+    light = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1).to(dev)
+    w = [torch.randn(M, generator=g).to(dev), torch.randn(M, 3, generator=g).to(dev), torch.randn(M, 3, generator=g).to(dev),
+         torch.randn(M, 3, generator=g).to(dev)]
+    grads = {}
+    old = (_lib.USE_TC, _lib.USE_TC_BWD)
+    try:
+        for tcb in (False, True):
+            _lib.USE_TC, _lib.USE_TC_BWD = True, tcb
+            _lib.PROFILE.reset()
+            _lib.PROFILE.enabled = True
+            m = make_model(sd, 0.9, dev).train()
+            xg = x.clone().requires_grad_(True)
+            sdf, sigma, color, normal, deform, raw = m(xg, t, light, ratio=1.0, shading='albedo_normal')
+            loss = (sdf * w[0]).sum() + (color * w[1]).sum() + (normal * w[2]).sum() + (deform * w[3]).sum() * 1e-3
+            loss.backward()
+            torch.cuda.synchronize()
+            launched = set(_lib.PROFILE.summary())
+            assert ('field_bwd_warp_tc' in launched) == tcb, launched      # the tensor-core kernel really ran (or not)
+            grads[tcb] = {'x': xg.grad.clone(), **{n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}}
+    finally:
+        _lib.USE_TC, _lib.USE_TC_BWD = old
+        _lib.PROFILE.enabled = False
+    errs = {n: rel_l2(cpu(grads[True][n]), cpu(grads[False][n])) for n in grads[False] if float(grads[False][n].abs().max()) > 0}
+    bad = {n: e for n, e in errs.items() if e > 2e-4}
+    assert not bad, f'{bad}\nall: {errs}'
