@@ -251,18 +251,32 @@ def main():
         value = N_RAYS / (ms_step * 1e-3)
         e2e_val = N_RAYS / (ms_e2e / args.steps * 1e-3)
         tf_peak, hbm_peak, which = peaks()
-        # dominant kernel: the fused backward of the main query (WARP|MAIN|COLOR|FD: 1 + 6 SDF queries), dgrad + wgrad = 2x forward MACs
+        # algorithmic FLOPs per launch (2 per MAC; backward = dgrad + wgrad = 2x forward; recompute is NOT counted)
         M_local = n_local * N_SAMPLES
-        macs_fwd_main = MAC_DEFORM + MAC_TOPO + MAC_COLOR + 7 * MAC_SDF
-        flops_bwd_main = 2 * 2 * macs_fwd_main * M_local
-        k = kern.get('field_bwd_main', None)
+        sdf_fd = 73 * 64 + 64 * 64 + 64           # an FD query only needs output row 0 of the last SDF layer
+        tc_bwd = 'field_bwd_warp_tc' in kern
+        flops = {
+            'field_fwd_main': 2 * (MAC_DEFORM + MAC_TOPO + MAC_COLOR + MAC_SDF + 6 * sdf_fd) * M_local,
+            'field_fwd_aux': 2 * 6 * sdf_fd * M_local,
+            'field_bwd_main': 4 * ((0 if tc_bwd else MAC_DEFORM + MAC_TOPO) + MAC_COLOR + MAC_SDF + 6 * sdf_fd) * M_local,
+            'field_bwd_aux': 4 * 6 * sdf_fd * M_local,
+            'field_bwd_warp_tc': 4 * (MAC_DEFORM + MAC_TOPO) * M_local,
+        }
+        engine = {'field_fwd_main': 'tcgen05 (3x fp16 split)', 'field_fwd_aux': 'tcgen05 (3x fp16 split)', 'field_bwd_warp_tc': 'tcgen05 (3x fp16 split)',
+                  'field_bwd_main': 'fp32 SIMT', 'field_bwd_aux': 'fp32 SIMT'}
+        rooflines = []
+        for name, fl in flops.items():
+            if name in kern:
+                ach = fl / (kern[name]['avg_ms'] * 1e-3) / 1e12
+                rooflines.append({'kernel': name, 'engine': engine[name], 'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s',
+                                  'frac': ach / tf_peak, 'traffic': None, 'avg_launch_ms': kern[name]['avg_ms'], 'launches_timed': kern[name]['n'],
+                                  'algorithmic_flops_per_launch': fl})
+        rooflines.sort(key=lambda r: -r['avg_launch_ms'])
         roof = None
-        if k:
-            ach = flops_bwd_main / (k['avg_ms'] * 1e-3) / 1e12
-            roof = {'kernel': 'field_bwd_kernel (main query)', 'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach / tf_peak,
-                    'traffic': None, 'peak_source': which, 'avg_launch_ms': k['avg_ms'], 'launches_timed': k['n'],
-                    'algorithmic_flops_per_launch': flops_bwd_main,
-                    'note': 'fp32 SIMT engine (round 1): its own ceiling is the fp32 FMA pipe (~72 TFLOP/s), see DESIGN.md'}
+        if rooflines:
+            roof = dict(rooflines[0], peak_source=which,
+                        note='dominant kernel by measured time; fp32-parity engine: tensor-core kernels spend 3 MMAs per product (fp16 hi/lo split), '
+                             'SIMT kernels are bounded by the 72 TFLOP/s fp32 FMA pipe; all kernels in "rooflines"')
         launches = sum(v['n'] for v in kern.values()) // max(kern_steps, 1) if kern else None
         cpu_val = None
         if args.cpu_baseline_steps > 0:
@@ -273,7 +287,7 @@ def main():
                 'config': dict(workload_config(world), cuda_graph=(not args.no_graph)), 'clocks': clocks,
                 'e2e': {'value': e2e_val, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
                 'gpu_launches': launches, 'kernels': kern, 'final_loss': last_loss,
-                'roofline': roof,
+                'roofline': roof, 'rooflines': rooflines,
                 'cpu_baseline': {'value': cpu_val, 'unit': 'rays/s', 'cores': cpu_threads(), 'kind': 'port',
                                  'sample': f'64 rays x {N_SAMPLES} samples (1/64 of the step), fwd+bwd+Adam, {args.cpu_baseline_steps} timed steps after 1 warm-up, oracle port on torch CPU'}}
         print(json.dumps(line))

@@ -65,6 +65,7 @@ class Renderer:
         # occupancy-grid march is replaced by the fixed-S lattice over the AABB chord (csrc/sampler.cu:uniform_kernel)
         self.uniform_samples = uniform_samples
         self.world_size = 1   # set by the data-parallel driver (bench.py / train.py)
+        self.sdf_count_override = None   # 0-dim tensor: pre-reduced global normaliser (lets the step be graph-captured without NCCL inside)
 
     @torch.no_grad()
     def sample_uniform(self, rays_o, rays_d, S, jitter=None):
@@ -164,7 +165,10 @@ class Renderer:
             if rays_depth is not None:
                 t_gt = rays_depth[ray_indices]
                 t_mask = rays_mask[ray_indices] if rays_mask is not None else None
-                cnt = global_count(torch.count_nonzero(t_gt), self.world_size) if self.world_size > 1 else None
+                if self.sdf_count_override is not None:
+                    cnt = self.sdf_count_override
+                else:
+                    cnt = global_count(torch.count_nonzero(t_gt), self.world_size) if self.world_size > 1 else None
                 fs_loss, sdf_loss = get_sdf_loss(t_positions, t_gt, sdf, tr['trunc'], mask=t_mask, rays_w_depth=cnt)
                 results['sdf_loss'], results['fs_loss'] = sdf_loss, fs_loss
         return results

@@ -113,25 +113,57 @@ def train_step(renderer, opt, batch, tr, world_size=1, shading='albedo_normal', 
     return loss.detach()
 
 
+def train_step_compute(renderer, opt, batch, tr, world_size=1, shading='albedo_normal'):
+    """zero-grad + render + loss + backward (no collective, no optimiser): the graph-capturable part of a sharded step"""
+    opt.zero_grad()
+    out = renderer.render_rays(batch['rays_o'], batch['rays_d'], batch['rays_t'], batch['rays_id'], bg_color=batch['bg'],
+                               shading=shading, real_view=True, rays_depth=batch['depth'], rays_mask=batch['mask'], optimize_pose=True)
+    loss = real_view_loss(out, batch, renderer.model, tr)
+    (loss / world_size).backward()
+    return loss.detach()
+
+
 class GraphedStep:
-    """The whole optimiser step (render forward, losses, backward, all-reduce, Adam) captured ONCE as a CUDA graph and
-    replayed per iteration: the ~1000 small launches of the host-side glue (parameter packing, indexing, loss heads)
-    cost no CPU time any more.  Inputs live in static device buffers (`self.batch`); shapes are fixed (fixed-S sampler),
-    RNG draws inside the step use torch's graph-safe Philox offsets, the Adam step count is device-resident."""
+    """The optimiser step captured as CUDA graphs and replayed per iteration: the ~1000 small launches of the host-side
+    glue (parameter packing, indexing, loss heads) cost no CPU time any more.  Inputs live in static device buffers
+    (`self.batch`); shapes are fixed (fixed-S sampler), RNG draws inside the step use torch's graph-safe Philox offsets,
+    the Adam step count is device-resident.  With world_size > 1 the NCCL exchanges stay OUTSIDE the graphs
+    (graph A: zero-grad/render/loss/backward -> eager all-reduce of the flat gradient buffer -> graph B: fused Adam);
+    the global loss normaliser (render.global_count) is reduced eagerly before graph A from the batch itself."""
 
     def __init__(self, renderer, opt, example_batch, tr, world_size=1, warmup=3):
         self.renderer, self.opt, self.tr, self.world = renderer, opt, tr, world_size
         self.batch = {k: v.clone() for k, v in example_batch.items()}
+        dev = self.batch['rays_o'].device
+        if world_size > 1:
+            renderer.sdf_count_override = torch.ones((), device=dev)
+        self._prepare()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                train_step(renderer, opt, self.batch, tr, world_size)
+                train_step_compute(renderer, opt, self.batch, tr, world_size)
+                opt.all_reduce()
+                opt.step()
+                renderer.model.invalidate()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = train_step(renderer, opt, self.batch, tr, world_size)
+        self.graph_a = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_a):
+            self.loss = train_step_compute(renderer, opt, self.batch, tr, world_size)
+        self.graph_b = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_b):
+            opt.step()
+        renderer.model.invalidate()
+
+    def _prepare(self):
+        """global count of samples with a depth observation (utils.py:107 normaliser) for the fixed-S sampler:
+        (#rays with depth > 0) * S, averaged over ranks (see render.global_count)"""
+        if self.world > 1:
+            from .render import global_count
+            S = self.renderer.uniform_samples
+            cnt = global_count(torch.count_nonzero(self.batch['depth']) * S, self.world)
+            self.renderer.sdf_count_override.copy_(cnt)
 
     def load(self, batch, non_blocking=True):
         for k, v in batch.items():
@@ -140,5 +172,8 @@ class GraphedStep:
     def step(self, batch=None):
         if batch is not None:
             self.load(batch)
-        self.graph.replay()
+        self._prepare()
+        self.graph_a.replay()
+        self.opt.all_reduce()
+        self.graph_b.replay()
         return self.loss

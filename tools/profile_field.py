@@ -21,6 +21,9 @@ for it in range(3):
     if mode == 'fwd':
         with torch.no_grad():
             out = m(x, t, light, ratio=1.0, shading='albedo_normal')
+    elif mode == 'aux':   # the perturbed-normal query of render_rays: 6 SDF queries, topo = None
+        n, raw = m.normal(x, topo=None)
+        n.sum().backward()
     else:
         xg = x.clone().requires_grad_(True)
         out = m(xg, t, light, ratio=1.0, shading='albedo_normal')
