@@ -1,0 +1,350 @@
+"""SDS guidance: B200-native restatement of `Zero123.train_step`
+(/root/reference/models/guidance/zero123_utils.py:56-296) and of the part of `ldm/` it executes:
+`UNetModel.forward` (ldm/modules/diffusionmodules/openaimodel.py:745-777 with ResBlock :256-276,
+SpatialTransformer / BasicTransformerBlock / CrossAttention ldm/modules/attention.py:152-266, GEGLU :37-64,
+timestep_embedding util.py:151-171), the VAE `Encoder.forward` (ldm/modules/diffusionmodules/model.py:434-459),
+`DiagonalGaussianDistribution.sample` (distributions.py:24-37), `get_first_stage_encoding` (ddpm.py:610-617),
+`cc_projection` (ddpm.py:526) and the 'hybrid' conditioning of `DiffusionWrapper` (ddpm.py:1459-1462).
+
+Design (not a port): the networks are *functions of the checkpoint's state_dict* -- the architecture is read off the
+parameter names (`model.diffusion_model.input_blocks.4.1.transformer_blocks.0.attn1.to_q.weight` ...), so the
+Zero-1-to-3 checkpoint (or any SD-1.x-shaped UNet / KL-VAE) loads without a module tree.  B200 specifics:
+  * the UNet runs under no_grad, batch 2 (CFG), and can be captured ONCE as a CUDA graph (`graph=True`);
+  * cross-attention over the single conditioning token collapses to `to_out(to_v(ctx))` broadcast over the queries
+    (softmax over one key == 1; attention.py:170-193), removing 16 of the 32 attention products;
+  * self-attention uses the fused scaled-dot-product kernel; weights stay resident (3.4 GB fp32 of 180 GB);
+  * the VAE-encoder weights are frozen (`requires_grad=False`), so backward is input-gradient only (the reference
+    also computes ~545 GFLOP of unused weight gradients because nothing freezes them, zero123_utils.py:52);
+  * the scalar chain (add-noise, CFG combine, w(t)(eps_hat - eps), nan_to_num) runs in two tiny kernels of the C ABI
+    (mb_add_noise, mb_sds_grad).
+Precision is fp32 like the reference (`fp16: False`); `precision='tf32'|'bf16'` are opt-in speed modes.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import check, ptr, stream
+
+
+# ------------------------------------------------------------------------------------------------
+# schedule (diffusers DDIMScheduler(1000, 0.00085, 0.012, 'scaled_linear'), zero123_utils.py:75-87)
+# ------------------------------------------------------------------------------------------------
+def alphas_cumprod(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012):
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+def timestep_embedding(t, dim, max_period=10000):
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+    args = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+def _gn(x, sd, prefix, eps):
+    return F.group_norm(x.float(), 32, sd[prefix + '.weight'], sd[prefix + '.bias'], eps).to(x.dtype)
+
+
+def _conv(x, sd, prefix, stride=1, padding=1):
+    return F.conv2d(x, sd[prefix + '.weight'], sd[prefix + '.bias'], stride=stride, padding=padding)
+
+
+def _lin(x, sd, prefix):
+    return F.linear(x, sd[prefix + '.weight'], sd.get(prefix + '.bias'))
+
+
+# ------------------------------------------------------------------------------------------------
+# UNet
+# ------------------------------------------------------------------------------------------------
+def _res_block(h, emb, sd, p):
+    x = h
+    h = _conv(F.silu(_gn(h, sd, p + '.in_layers.0', 1e-5)), sd, p + '.in_layers.2')
+    h = h + _lin(F.silu(emb), sd, p + '.emb_layers.1')[:, :, None, None]
+    h = _conv(F.silu(_gn(h, sd, p + '.out_layers.0', 1e-5)), sd, p + '.out_layers.3')
+    if p + '.skip_connection.weight' in sd:
+        x = _conv(x, sd, p + '.skip_connection', padding=0)
+    return x + h
+
+
+def _attention(x, ctx, sd, p, heads=8):
+    """CrossAttention (attention.py:152-193).  ctx None -> self-attention; a single context token collapses analytically."""
+    B, T, C = x.shape
+    if ctx is not None and ctx.shape[1] == 1:
+        v = F.linear(ctx, sd[p + '.to_v.weight'])                      # [B,1,C]: softmax over one key is 1
+        return _lin(v, sd, p + '.to_out.0').expand(B, T, C)
+    src = x if ctx is None else ctx
+    q = F.linear(x, sd[p + '.to_q.weight']).view(B, T, heads, C // heads).transpose(1, 2)
+    k = F.linear(src, sd[p + '.to_k.weight']).view(B, src.shape[1], heads, C // heads).transpose(1, 2)
+    v = F.linear(src, sd[p + '.to_v.weight']).view(B, src.shape[1], heads, C // heads).transpose(1, 2)
+    o = F.scaled_dot_product_attention(q, k, v)                          # scale = d_head^-0.5
+    return _lin(o.transpose(1, 2).reshape(B, T, C), sd, p + '.to_out.0')
+
+
+def _spatial_transformer(h, ctx, sd, p):
+    B, C, H, W = h.shape
+    x = F.group_norm(h, 32, sd[p + '.norm.weight'], sd[p + '.norm.bias'], 1e-6)
+    x = _conv(x, sd, p + '.proj_in', padding=0).flatten(2).transpose(1, 2)          # b (hw) c
+    i = 0
+    while f'{p}.transformer_blocks.{i}.norm1.weight' in sd:
+        q = f'{p}.transformer_blocks.{i}'
+        ln = lambda z, n: F.layer_norm(z, (C,), sd[f'{q}.{n}.weight'], sd[f'{q}.{n}.bias'])
+        x = _attention(ln(x, 'norm1'), None, sd, q + '.attn1') + x
+        x = _attention(ln(x, 'norm2'), ctx, sd, q + '.attn2') + x
+        g = _lin(ln(x, 'norm3'), sd, q + '.ff.net.0.proj')
+        a, gate = g.chunk(2, dim=-1)
+        x = _lin(a * F.gelu(gate), sd, q + '.ff.net.2') + x
+        i += 1
+    x = x.transpose(1, 2).reshape(B, C, H, W)
+    return _conv(x, sd, p + '.proj_out', padding=0) + h
+
+
+class _KeyIndex(dict):
+    """state_dict view with a cached prefix test (the functional nets probe names a lot)"""
+
+    def __init__(self, sd):
+        super().__init__(sd)
+        self._prefixes = set()
+        for k in sd:
+            parts = k.split('.')
+            for i in range(1, len(parts)):
+                self._prefixes.add('.'.join(parts[:i]) + '.')
+
+    def has_prefix(self, p):
+        return p in self._prefixes
+
+
+def unet_forward(sd, x, t, ctx, model_channels=320):
+    """UNetModel.forward(x [B,8,h,w], timesteps [B], context [B,1,768]) -> [B,4,h,w]; sd keys without the
+    'model.diffusion_model.' prefix."""
+    emb = _lin(F.silu(_lin(timestep_embedding(t, model_channels), sd, 'time_embed.0')), sd, 'time_embed.2')
+    hs, h = [], x
+    i = 0
+    while sd.has_prefix(f'input_blocks.{i}.'):
+        h = _unet_block_fast(h, emb, ctx, sd, f'input_blocks.{i}')
+        hs.append(h)
+        i += 1
+    h = _unet_block_fast(h, emb, ctx, sd, 'middle_block')
+    i = 0
+    while sd.has_prefix(f'output_blocks.{i}.'):
+        h = _unet_block_fast(torch.cat([h, hs.pop()], dim=1), emb, ctx, sd, f'output_blocks.{i}')
+        i += 1
+    return _conv(F.silu(_gn(h, sd, 'out.0', 1e-5)), sd, 'out.2')
+
+
+def _unet_block_fast(h, emb, ctx, sd, p):
+    j = 0
+    while sd.has_prefix(f'{p}.{j}.'):
+        q = f'{p}.{j}'
+        if q + '.in_layers.0.weight' in sd:
+            h = _res_block(h, emb, sd, q)
+        elif q + '.proj_in.weight' in sd:
+            h = _spatial_transformer(h, ctx, sd, q)
+        elif q + '.op.weight' in sd:
+            h = _conv(h, sd, q + '.op', stride=2)
+        elif q + '.conv.weight' in sd:
+            h = _conv(F.interpolate(h, scale_factor=2, mode='nearest'), sd, q + '.conv')
+        else:
+            h = _conv(h, sd, q)
+        j += 1
+    return h
+
+
+# ------------------------------------------------------------------------------------------------
+# VAE encoder (model.py:368-459) + quant_conv (autoencoder.py:302,324-328)
+# ------------------------------------------------------------------------------------------------
+def _vae_res(x, sd, p):
+    h = _conv(F.silu(_gn(x, sd, p + '.norm1', 1e-6)), sd, p + '.conv1')
+    h = _conv(F.silu(_gn(h, sd, p + '.norm2', 1e-6)), sd, p + '.conv2')
+    if p + '.nin_shortcut.weight' in sd:
+        x = _conv(x, sd, p + '.nin_shortcut', padding=0)
+    return x + h
+
+
+def _vae_attn(x, sd, p):
+    B, C, H, W = x.shape
+    h = _gn(x, sd, p + '.norm', 1e-6)
+    q = _conv(h, sd, p + '.q', padding=0).flatten(2).transpose(1, 2)[:, None]       # [B,1,HW,C]
+    k = _conv(h, sd, p + '.k', padding=0).flatten(2).transpose(1, 2)[:, None]
+    v = _conv(h, sd, p + '.v', padding=0).flatten(2).transpose(1, 2)[:, None]
+    o = F.scaled_dot_product_attention(q, k, v)[:, 0].transpose(1, 2).reshape(B, C, H, W)   # scale c^-0.5
+    return x + _conv(o, sd, p + '.proj_out', padding=0)
+
+
+def vae_encode_moments(sd, img):
+    """Encoder.forward + quant_conv: img [B,3,256,256] in [-1,1] -> moments [B,8,32,32]; keys without 'first_stage_model.'"""
+    h = _conv(img, sd, 'encoder.conv_in')
+    lvl = 0
+    while sd.has_prefix(f'encoder.down.{lvl}.'):
+        b = 0
+        while sd.has_prefix(f'encoder.down.{lvl}.block.{b}.'):
+            h = _vae_res(h, sd, f'encoder.down.{lvl}.block.{b}')
+            b += 1
+        if f'encoder.down.{lvl}.downsample.conv.weight' in sd:   # zero-pad (0,1,0,1) then 3x3 stride-2 conv (model.py:60-79)
+            h = _conv(F.pad(h, (0, 1, 0, 1)), sd, f'encoder.down.{lvl}.downsample.conv', stride=2, padding=0)
+        lvl += 1
+    h = _vae_res(h, sd, 'encoder.mid.block_1')
+    h = _vae_attn(h, sd, 'encoder.mid.attn_1')
+    h = _vae_res(h, sd, 'encoder.mid.block_2')
+    h = _conv(F.silu(_gn(h, sd, 'encoder.norm_out', 1e-6)), sd, 'encoder.conv_out')
+    return _conv(h, sd, 'quant_conv', padding=0)
+
+
+# ------------------------------------------------------------------------------------------------
+class Zero123(torch.nn.Module):
+    """Same call surface as the reference wrapper (zero123_utils.py:56): `train_step`, `angle_between`, `update_t_range`,
+    `encode_imgs`, `get_img_embeds` (VAE half; the CLIP image embedder is init-time only and out of scope)."""
+
+    SCALE_FACTOR = 0.18215
+
+    def __init__(self, device, fp16=False, config=None, ckpt=None, vram_O=False, t_range=(0.02, 0.98), opt=None, state_dict=None,
+                 precision='fp32', graph=False):
+        super().__init__()
+        self.device, self.fp16, self.vram_O, self.t_range, self.opt = device, fp16, vram_O, list(t_range), opt
+        if state_dict is None:
+            if ckpt is None:
+                raise RuntimeError('Zero123: pass ckpt= (path to the Zero-1-to-3 checkpoint) or state_dict=')
+            state_dict = torch.load(ckpt, map_location='cpu')
+            state_dict = state_dict.get('state_dict', state_dict)
+        def sub(prefix):
+            return _KeyIndex({k[len(prefix):]: v.to(device).float().requires_grad_(False) for k, v in state_dict.items() if k.startswith(prefix)})
+        self.unet = sub('model.diffusion_model.')
+        self.vae = sub('first_stage_model.')
+        self.cc = sub('cc_projection.')
+        if not self.unet or not self.vae or not self.cc:
+            raise RuntimeError('Zero123: checkpoint lacks model.diffusion_model.* / first_stage_model.* / cc_projection.* weights')
+        self.num_train_timesteps = 1000
+        self.alphas = alphas_cumprod().to(device)
+        self.min_step = int(self.num_train_timesteps * self.t_range[0])
+        self.max_step = int(self.num_train_timesteps * self.t_range[1])
+        self.precision = precision
+        self.graph = graph
+        self._graph = None
+
+    def update_t_range(self, t_range):
+        self.t_range = t_range
+        self.min_step = int(self.num_train_timesteps * t_range[0])
+        self.max_step = int(self.num_train_timesteps * t_range[1])
+
+    # -- zero123_utils.py:102-120, vectorised (the reference loops in Python on the CPU) ----------------
+    @staticmethod
+    def angle_between(sph_v1, sph_v2):
+        def cart(s):
+            r, th, ph = s[..., 0], s[..., 1], s[..., 2]
+            return torch.stack([r * torch.sin(th) * torch.cos(ph), r * torch.sin(th) * torch.sin(ph), r * torch.cos(th)], -1)
+        a, b = cart(sph_v1.float().cpu()), cart(sph_v2.float().cpu())
+        a, b = a / a.norm(dim=-1, keepdim=True), b / b.norm(dim=-1, keepdim=True)
+        return torch.arccos(torch.clip(a @ b.t(), -1.0, 1.0))
+
+    # -- VAE ---------------------------------------------------------------------------------------------
+    def encode_imgs(self, imgs, noise=None):
+        """zero123_utils.py:285-290 + ddpm.py:610-617: posterior SAMPLE * scale_factor; grad flows to imgs."""
+        moments = vae_encode_moments(self.vae, imgs * 2 - 1)
+        mean, logvar = moments.chunk(2, dim=1)
+        std = torch.exp(0.5 * logvar.clamp(-30.0, 20.0))
+        if noise is None:
+            noise = torch.randn(mean.shape).to(mean.device)          # the reference draws on the CPU (distributions.py:36)
+        return self.SCALE_FACTOR * (mean + std * noise)
+
+    @torch.no_grad()
+    def get_img_embeds(self, x, clip_embedder=None):
+        """zero123_utils.py:90-100.  c (CLIP ViT-L/14 image embedding) needs `clip_embedder`; v is the VAE posterior mode."""
+        v = [vae_encode_moments(self.vae, (xx * 2 - 1).unsqueeze(0)).chunk(2, dim=1)[0] for xx in x]
+        if clip_embedder is None:
+            raise NotImplementedError('the CLIP image embedder is init-time only and is not part of the hot path; pass clip_embedder=')
+        c = [clip_embedder((xx * 2 - 1).unsqueeze(0)) for xx in x]
+        return c, v
+
+    # -- the UNet leg: noise prediction with classifier-free guidance -> SDS gradient -------------------------------
+    @torch.no_grad()
+    def sds_grad(self, latents, noise, t, c_crossattn, c_concat, T, guidance_scale, grad_scale_w):
+        """zero123_utils.py:177-212 for one reference view: add_noise -> UNet(x2, CFG) -> grad_scale*w(t)*(eps_hat - eps).
+        t: LongTensor [1]; grad_scale_w: 0-dim/[1] tensor = grad_scale * (1 - abar_t)."""
+        L = _lib.lib()
+        lat = latents.detach().contiguous().float()
+        noise = noise.contiguous().float()
+        ab = self.alphas[t].reshape(())
+        noisy = torch.empty_like(lat)
+        check(L.mb_add_noise(ptr(lat), ptr(noise), _lib.C.c_float(float(ab.sqrt())), _lib.C.c_float(float((1 - ab).sqrt())), ptr(noisy),
+                             lat.numel(), stream()), 'add_noise')
+        clip_emb = F.linear(torch.cat([c_crossattn, T], dim=-1), self.cc['weight'], self.cc['bias'])       # ddpm.py:526 Linear(772, 768)
+        ctx = torch.cat([torch.zeros_like(clip_emb), clip_emb], dim=0)                                       # [2,1,768]
+        cc = torch.cat([torch.zeros_like(c_concat), c_concat], dim=0)                                        # [2,4,32,32]
+        x_in = torch.cat([torch.cat([noisy] * 2), cc], dim=1)                                                # 'hybrid': channel concat
+        t_in = torch.cat([t] * 2)
+        eps = self._unet(x_in, t_in, ctx)
+        eu, ec = eps[0:1].contiguous(), eps[1:2].contiguous()
+        grad = torch.empty_like(lat)
+        check(L.mb_sds_grad(ptr(eu), ptr(ec), ptr(noise), _lib.C.c_float(float(guidance_scale)), _lib.C.c_float(float(grad_scale_w)),
+                            ptr(grad), lat.numel(), stream()), 'sds_grad')
+        return grad
+
+    def _unet(self, x_in, t_in, ctx):
+        if self.precision == 'bf16':
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                return unet_forward(self.unet, x_in, t_in, ctx).float()
+        if not self.graph:
+            return unet_forward(self.unet, x_in, t_in, ctx)
+        if self._graph is None:            # capture once: static inputs, replay afterwards
+            self._gx, self._gt, self._gc = x_in.clone(), t_in.clone(), ctx.clone()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                unet_forward(self.unet, self._gx, self._gt, self._gc)
+            torch.cuda.current_stream().wait_stream(s)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._gout = unet_forward(self.unet, self._gx, self._gt, self._gc)
+        self._gx.copy_(x_in); self._gt.copy_(t_in); self._gc.copy_(ctx)
+        self._graph.replay()
+        return self._gout
+
+    # -- zero123_utils.py:138-236 ---------------------------------------------------------------------------------------
+    def train_step(self, embeddings, pred_rgb, polar, azimuth, radius, guidance_scale=3, as_latent=False, grad_scale=1,
+                   save_guidance_path=None, t=None, last_grad_scale=None, noise=None, vae_noise=None):
+        dev = pred_rgb.device
+        ref_radii, ref_polars, ref_azimuths = embeddings['ref_radii'], embeddings['ref_polars'], embeddings['ref_azimuths']
+        polar, azimuth, radius = (torch.as_tensor(v, dtype=torch.float32).reshape(-1).cpu() for v in (polar, azimuth, radius))
+        v1 = torch.stack([radius + ref_radii[0], torch.deg2rad(polar + ref_polars[0]), torch.deg2rad(azimuth + ref_azimuths[0])], dim=-1)
+        v2 = torch.stack([torch.tensor(ref_radii, dtype=torch.float32), torch.deg2rad(torch.tensor(ref_polars, dtype=torch.float32)),
+                          torch.deg2rad(torch.tensor(ref_azimuths, dtype=torch.float32))], dim=-1)
+        angles = torch.rad2deg(self.angle_between(v1, v2)).to(dev)
+        grad_scale = (torch.exp(angles.min(dim=1)[0] / (180 / len(ref_azimuths))) - 1) * grad_scale
+        if as_latent:
+            latents = F.interpolate(pred_rgb, (32, 32), mode='bilinear', align_corners=False) * 2 - 1
+        else:
+            latents = self.encode_imgs(F.interpolate(pred_rgb, (256, 256), mode='bilinear', align_corners=False), noise=vae_noise)
+        if t is None:
+            t = torch.randint(self.min_step, self.max_step + 1, (latents.shape[0],), dtype=torch.long, device=dev)
+        if len(ref_azimuths) > 1:
+            inv = 1 / angles
+            inv[inv > 100] = 100
+            inv /= inv.max(dim=-1, keepdim=True)[0]
+            inv[inv < 0.1] = 0
+        else:
+            inv = torch.tensor([1.0], device=dev)
+        ws = torch.tensor(embeddings['zero123_ws'], dtype=torch.float32, device=dev)[None, :] * inv
+        ws /= ws.max(dim=-1, keepdim=True)[0]
+        ws[ws < 0.1] = 0
+        if noise is None:
+            noise = torch.randn_like(latents)
+        w = 1 - self.alphas[t]
+        gsw = (grad_scale * w).reshape(-1)
+        total = torch.zeros_like(latents)
+        # sum_i ws_i * eps_hat_i / sum ws  -  eps   ==  sum_i (ws_i / sum ws) * (eps_hat_i - eps): apply the grad kernel per view
+        wsum = ws.sum(dim=-1)
+        for i, (c_crossattn, c_concat) in enumerate(zip(embeddings['c_crossattn'], embeddings['c_concat'])):
+            wi = float(ws[0, i] / wsum[0])
+            if wi == 0.0:
+                continue
+            p = polar + ref_polars[0] - ref_polars[i]
+            a = azimuth + ref_azimuths[0] - ref_azimuths[i]
+            a = torch.where(a > 180, a - 360, a)
+            r = radius + ref_radii[0] - ref_radii[i]
+            T = torch.stack([torch.deg2rad(p), torch.sin(torch.deg2rad(a)), torch.cos(torch.deg2rad(a)), r], dim=-1)[:, None, :].to(dev)
+            total += wi * self.sds_grad(latents, noise, t, c_crossattn.to(dev).reshape(1, 1, -1), c_concat.to(dev), T, guidance_scale, gsw[0])
+        grad = torch.nan_to_num(total)
+        targets = (latents - grad).detach()
+        loss = 0.5 * F.mse_loss(latents.float(), targets, reduction='sum') / latents.shape[0]     # d loss / d latents == grad
+        return loss, t, grad_scale, noise
