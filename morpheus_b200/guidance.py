@@ -191,6 +191,24 @@ def vae_encode_moments(sd, img):
     return _conv(h, sd, 'quant_conv', padding=0)
 
 
+class _precision:
+    """'fp32': true fp32 convolutions / matmuls (cuDNN would otherwise pick TF32 for convs by default, ~2e-3 error on the
+    SDS gradient); 'tf32': allow TF32 tensor-core paths (what stock PyTorch does for the reference on Ampere+); 'bf16': autocast."""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        allow = self.mode != 'fp32'
+        torch.backends.cudnn.allow_tf32 = allow
+        torch.backends.cuda.matmul.allow_tf32 = allow
+
+    def __exit__(self, *exc):
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False
+
+
 # ------------------------------------------------------------------------------------------------
 class Zero123(torch.nn.Module):
     """Same call surface as the reference wrapper (zero123_utils.py:56): `train_step`, `angle_between`, `update_t_range`,
@@ -240,7 +258,8 @@ class Zero123(torch.nn.Module):
     # -- VAE ---------------------------------------------------------------------------------------------
     def encode_imgs(self, imgs, noise=None):
         """zero123_utils.py:285-290 + ddpm.py:610-617: posterior SAMPLE * scale_factor; grad flows to imgs."""
-        moments = vae_encode_moments(self.vae, imgs * 2 - 1)
+        with _precision(self.precision):
+            moments = vae_encode_moments(self.vae, imgs * 2 - 1)
         mean, logvar = moments.chunk(2, dim=1)
         std = torch.exp(0.5 * logvar.clamp(-30.0, 20.0))
         if noise is None:
@@ -281,6 +300,10 @@ class Zero123(torch.nn.Module):
         return grad
 
     def _unet(self, x_in, t_in, ctx):
+        with _precision(self.precision):
+            return self._unet_impl(x_in, t_in, ctx)
+
+    def _unet_impl(self, x_in, t_in, ctx):
         if self.precision == 'bf16':
             with torch.autocast('cuda', dtype=torch.bfloat16):
                 return unet_forward(self.unet, x_in, t_in, ctx).float()

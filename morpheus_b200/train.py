@@ -123,6 +123,33 @@ def train_step_compute(renderer, opt, batch, tr, world_size=1, shading='albedo_n
     return loss.detach()
 
 
+def virtual_view_step(renderer, guidance, opt, view, embeddings, tr, shading='lambertian', ambient_ratio=0.5, bg_color=None,
+                      guidance_scale=5.0, grad_weight=0.01, t=None, noise=None, vae_noise=None, light_d=None, world_size=1):
+    """One novel-view (SDS) optimiser step: morpheus.py:1147-1236 with real_view=False + get_virtual_view_loss (:1044-1088,
+    single reference view) + the regularisers that are live on virtual views (orientation x ori_weight, normal_smooth_3d,
+    code_reg, beta).  `view` comes from rays.virtual_view_rays."""
+    model = renderer.model
+    opt.zero_grad()
+    H, W = view['H'], view['W']
+    out = renderer.render_rays(view['rays_o'], view['rays_d'], view['rays_t'], view['rays_id'], H, W, bg_color=bg_color,
+                               ambient_ratio=ambient_ratio, light_d=light_d, shading=shading, real_view=False, optimize_pose=False)
+    pred_rgb = out['image'].reshape(1, H, W, 3).permute(0, 3, 1, 2).contiguous()
+    loss, t, grad_scale, noise = guidance.train_step(embeddings, pred_rgb, view['polar'], view['azimuth'], view['radius'],
+                                                     guidance_scale=guidance_scale, grad_scale=grad_weight, t=t, noise=noise, vae_noise=vae_noise)
+    if 'loss_orient' in out:
+        loss = loss + tr['ori_weight'] * out['loss_orient']
+    if 'loss_normal_perturb' in out:
+        loss = loss + tr['normal_smooth_3d'] * out['loss_normal_perturb']
+    if 'loss_code' in out:
+        loss = loss + tr['code_reg'] * out['loss_code']
+    loss = loss + tr['beta_weight'] * torch.mean(model.sdf2density.get_beta())
+    (loss / world_size).backward()
+    opt.all_reduce()
+    opt.step()
+    model.invalidate()
+    return loss.detach(), out
+
+
 class GraphedStep:
     """The optimiser step captured as CUDA graphs and replayed per iteration: the ~1000 small launches of the host-side
     glue (parameter packing, indexing, loss heads) cost no CPU time any more.  Inputs live in static device buffers

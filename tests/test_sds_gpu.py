@@ -46,7 +46,8 @@ def test_train_step_vs_oracle(graph):
         pg = pred.clone().to(dev).requires_grad_(True)
         loss, t_out, gs, noise_out = z123.train_step(emb, pg, polar, azimuth, radius, guidance_scale=5, grad_scale=0.01, t=t.to(dev),
                                                      noise=noise.to(dev), vae_noise=vae_noise.to(dev))
-        loss.backward()
+        with guidance._precision('fp32'):      # the VAE backward convolutions must not drop to TF32 either
+            loss.backward()
     # ---- oracle chain on the CPU (same functional nets are validated against the reference classes in test_sds_cpu.py) ----
     unet = guidance._KeyIndex({k[len('model.diffusion_model.'):]: v for k, v in sd.items() if k.startswith('model.diffusion_model.')})
     vae = guidance._KeyIndex({k[len('first_stage_model.'):]: v for k, v in sd.items() if k.startswith('first_stage_model.')})
@@ -69,3 +70,44 @@ def test_train_step_vs_oracle(graph):
     assert abs(float(gs) - float(grad_scale)) < 1e-6 * max(1.0, abs(float(grad_scale)))
     assert rel(loss, lo) < 1e-3
     assert rel(pg.grad, pc.grad) < 1e-3, rel(pg.grad, pc.grad)     # d loss / d pred_rgb: SDS gradient pulled through the VAE encoder
+
+
+def test_virtual_view_step_end_to_end():
+    """BASELINE cfg-3: 72x72 novel view -> occupancy-grid sampling -> fused render (lambertian) -> pred_rgb -> SDS -> backward
+    through compositing and the field kernels -> fused Adam.  Checks that the SDS gradient reaches the scene parameters."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from morpheus_b200 import guidance, rays
+    from morpheus_b200 import train as mtrain
+    from morpheus_b200.model import scene_representation
+    from morpheus_b200.nerfacc_compat import OccGridEstimator
+    from morpheus_b200.render import Renderer
+    dev = torch.device('cuda:0')
+    table = load_key_table()
+    sd = {}
+    sd.update(seeded_state(table['unet'], 1, 'model.diffusion_model.'))
+    sd.update(seeded_state(table['encoder'], 2, 'first_stage_model.encoder.'))
+    sd.update(seeded_state(table['quant_conv'], 3, 'first_stage_model.quant_conv.'))
+    sd.update(seeded_state(table['cc_projection'], 4, 'cc_projection.'))
+    z123 = guidance.Zero123(dev, state_dict=sd, t_range=[0.02, 0.5], precision='tf32')
+    torch.manual_seed(0)
+    cfg = {'model': {'bg_radius': 1.4, 'activation': 'exp'}, 'render': {'step_size': 0.01}, 'train': dict(mtrain.DEFAULT_TRAIN_CFG)}
+    model = scene_representation(cfg, 1.01, num_frames=200, deform_dim=16, use_app=False, use_t=False, amb_dim=2, color_grid=True,
+                                 use_joint=True, encode_topo=False).to(dev).train()
+    model.max_level = 0.75
+    est = OccGridEstimator(torch.tensor([-1.01] * 3 + [1.01] * 3), 128).to(dev).train()
+    R = Renderer(model, est, cfg, 200)
+    opt = mtrain.FlatAdam(model, 5e-4)
+    view = rays.virtual_view_rays(frame=12, num_frames=200, H=360, W=360, focal=517.0, scale=0.2, generator=torch.Generator().manual_seed(1), device=dev)
+    R.update_occ_grid(view['rays_t'].reshape(-1, 1), step=0)                       # morpheus.py:1189 (first refresh covers all 128^3 cells)
+    assert 0 < int(est.binaries.sum()) < 128 ** 3
+    g = torch.Generator().manual_seed(2)
+    emb = {'c_crossattn': [torch.randn(1, 1, 768, generator=g)], 'c_concat': [torch.randn(1, 4, 32, 32, generator=g)],
+           'ref_radii': [2.5], 'ref_polars': [90.0], 'ref_azimuths': [0.0], 'zero123_ws': [1]}
+    before = opt.flat.clone()
+    loss, out = mtrain.virtual_view_step(R, z123, opt, view, emb, cfg['train'], shading='lambertian', ambient_ratio=0.4,
+                                         bg_color=torch.rand(3, device=dev))
+    torch.cuda.synchronize()
+    assert out['image'].shape == (1, 72 * 72, 3) and torch.isfinite(loss)
+    assert torch.isfinite(opt.grad).all() and float(opt.grad.abs().max()) > 0
+    assert float((opt.flat - before).abs().max()) > 0
