@@ -12,14 +12,20 @@ namespace mb {
 constexpr int BWD_TM = 32;
 constexpr int BWD_P = 36;
 
-struct BwdSmem {
+// SMALL = the deform/topology backward is not done here (no WARP, or MB_F_SKIP_WARP_BWD with the tensor-core kernel):
+// only the SDF / colour activations (400 rows) and 80-row gradient buffers are needed -> 99 KB -> 2 CTAs per SM.
+template <bool SMALL>
+struct BwdSmemT {
     static constexpr int P = BWD_P;
-    static constexpr int STORE = 0;                    // [640][P] stored activations
-    static constexpr int IN0 = STORE + 640 * P;        // [96][P]
-    static constexpr int GIN0 = IN0 + 96 * P;          // [96][P]
-    static constexpr int DZA = GIN0 + 96 * P;          // [128][P]
-    static constexpr int DZB = DZA + 128 * P;          // [128][P]
-    static constexpr int WBUF = DZB + 128 * P;
+    static constexpr int STORE_ROWS = SMALL ? 400 : 640;
+    static constexpr int IN_ROWS = SMALL ? 0 : 96;
+    static constexpr int DZ_ROWS = SMALL ? 80 : 128;
+    static constexpr int STORE = 0;                    // stored activations
+    static constexpr int IN0 = STORE + STORE_ROWS * P;
+    static constexpr int GIN0 = IN0 + IN_ROWS * P;
+    static constexpr int DZA = GIN0 + IN_ROWS * P;
+    static constexpr int DZB = DZA + DZ_ROWS * P;
+    static constexpr int WBUF = DZB + DZ_ROWS * P;
     static constexpr int SX = WBUF + WBUF_FLOATS;      // [3][P]
     static constexpr int SXW = SX + 3 * P;
     static constexpr int SPT = SXW + 3 * P;
@@ -112,8 +118,10 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return s;  // valid in thread 0
 }
 
-__global__ void __launch_bounds__(FT, 1) field_bwd_kernel(const mb_field_params p, const mb_field_io io, const mb_field_grads gr) {
+template <bool SMALL>
+__global__ void __launch_bounds__(FT, SMALL ? 2 : 1) field_bwd_kernel(const mb_field_params p, const mb_field_io io, const mb_field_grads gr) {
     constexpr int TM = BWD_TM, P = BWD_P;
+    using BwdSmem = BwdSmemT<SMALL>;
     extern __shared__ __align__(16) float sm[];
     float* store = sm + BwdSmem::STORE;
     float* in0 = sm + BwdSmem::IN0;
@@ -374,7 +382,8 @@ __global__ void __launch_bounds__(FT, 1) field_bwd_kernel(const mb_field_params 
                 const int m = idx / 2, a = idx - m * 2;
                 if (m < nv) gr.g_topo_out[(size_t)m0 * 2 + idx] = gtopo[a * P + m];
             }
-        } else if (flags & MB_F_WARP) {
+        } else if (!SMALL && (flags & MB_F_WARP)) {
+          if constexpr (!SMALL) {
             build_freq<TM, P>(sx, in0, (int)p.n_freq);
             build_code_b<TM, P>(p, st, in0 + 39 * P);
             zero_rows_b<TM, P>(in0, 87, 96);
@@ -461,6 +470,7 @@ __global__ void __launch_bounds__(FT, 1) field_bwd_kernel(const mb_field_params 
                 }
             }
             __syncthreads();
+          }   // if constexpr (!SMALL)
         }
         // ---- outputs ----
         for (int idx = tid; idx < 3 * TM; idx += FT) {
@@ -492,15 +502,27 @@ extern "C" int mb_field_backward(const mb_field_params* p, const mb_field_io* io
     if ((io->flags & (MB_F_MAIN | MB_F_FD)) && !g->g_emb_sdf) { set_error("field_backward: g_emb_sdf is null"); return MB_EINVAL; }
     if ((io->flags & MB_F_COLOR) && !g->g_emb_col) { set_error("field_backward: g_emb_col is null"); return MB_EINVAL; }
     if ((io->flags & MB_F_TOPO_IN) && !io->topo_in) { set_error("field_backward: TOPO_IN needs topo_in"); return MB_EINVAL; }
-    constexpr size_t smem = (size_t)BwdSmem::TOTAL * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(field_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("field_backward: cannot reserve %zu B smem: %s", smem, cudaGetErrorString(e)); return MB_ECUDA; }
-        attr_set = true;
-    }
     const uint32_t n_tiles = div_up(io->M, BWD_TM);
-    const uint32_t grid = min(n_tiles, (uint32_t)mb_sm_count());
-    field_bwd_kernel<<<grid, FT, smem, (cudaStream_t)stream>>>(*p, *io, *g);
+    const bool small = !(io->flags & MB_F_WARP) || (io->flags & MB_F_SKIP_WARP_BWD);
+    static bool attr_set[2] = {false, false};
+    if (small) {
+        constexpr size_t smem = (size_t)BwdSmemT<true>::TOTAL * sizeof(float);
+        if (!attr_set[1]) {
+            cudaError_t e = cudaFuncSetAttribute(field_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("field_backward: cannot reserve %zu B smem: %s", smem, cudaGetErrorString(e)); return MB_ECUDA; }
+            attr_set[1] = true;
+        }
+        const uint32_t grid = min(n_tiles, (uint32_t)mb_sm_count() * 2u);
+        field_bwd_kernel<true><<<grid, FT, smem, (cudaStream_t)stream>>>(*p, *io, *g);
+    } else {
+        constexpr size_t smem = (size_t)BwdSmemT<false>::TOTAL * sizeof(float);
+        if (!attr_set[0]) {
+            cudaError_t e = cudaFuncSetAttribute(field_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("field_backward: cannot reserve %zu B smem: %s", smem, cudaGetErrorString(e)); return MB_ECUDA; }
+            attr_set[0] = true;
+        }
+        const uint32_t grid = min(n_tiles, (uint32_t)mb_sm_count());
+        field_bwd_kernel<false><<<grid, FT, smem, (cudaStream_t)stream>>>(*p, *io, *g);
+    }
     return check_launch("field_backward");
 }
