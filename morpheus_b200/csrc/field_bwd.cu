@@ -149,8 +149,11 @@ __global__ void __launch_bounds__(FT, SMALL ? 2 : 1) field_bwd_kernel(const mb_f
     float* GA = gr.g_arena;
     const uint32_t flags = io.flags;
     const bool topo_live = (flags & (MB_F_WARP | MB_F_TOPO_IN)) != 0;
-    const GridCtx gs{p.emb_sdf, p.offsets, p.S, p.H, p.n_levels, p.bound, p.two_bound};
-    const GridCtx gc{p.emb_col, p.offsets, p.S, p.H, p.n_levels, p.bound, p.two_bound};
+    __shared__ LevelInfo s_levels[16];
+    if (p.offsets) init_levels(s_levels, p.offsets, p.S, p.H);
+    __syncthreads();
+    const GridCtx gs{p.emb_sdf, p.offsets, p.S, p.H, p.n_levels, p.bound, p.two_bound, s_levels};
+    const GridCtx gc{p.emb_col, p.offsets, p.S, p.H, p.n_levels, p.bound, p.two_bound, s_levels};
 
     const uint32_t n_tiles = div_up(io.M, TM);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {

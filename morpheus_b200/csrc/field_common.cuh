@@ -204,6 +204,15 @@ __device__ __forceinline__ void freq_backward(const float* __restrict__ sp, cons
     }
 }
 
+// per-level constants, computed once per CTA (the reference kernel re-derives them per (sample, level): gridencoder.cu:132-133)
+struct LevelInfo {
+    uint32_t res;        // ceil(exp2f(l*S)*H) in float32
+    uint32_t size;       // hashmap_size = offsets[l+1]-offsets[l]
+    uint32_t off;        // offsets[l]
+    uint32_t mask;       // size-1 when size is a power of two (index % size == index & mask), else 0
+    uint32_t hashed;     // get_grid_index falls through to the hash (stride > hashmap_size after the dense walk)
+};
+
 struct GridCtx {
     const float* emb;
     const int32_t* offsets;
@@ -211,7 +220,34 @@ struct GridCtx {
     uint32_t H;
     uint32_t n_levels;
     float bound, two_bound;
+    const LevelInfo* lv;   // [16] in shared memory
 };
+
+// threads 0..15 fill the table; caller synchronises
+__device__ __forceinline__ void init_levels(LevelInfo* lv, const int32_t* __restrict__ offsets, float S, uint32_t H) {
+    const int l = threadIdx.x;
+    if (l < 16) {
+        LevelInfo v;
+        v.res = level_resolution(l, S, H);
+        v.off = (uint32_t)offsets[l];
+        v.size = (uint32_t)offsets[l + 1] - v.off;
+        v.mask = (v.size & (v.size - 1)) == 0 ? v.size - 1 : 0;
+        const unsigned long long r = v.res;
+        // dense walk of get_grid_index (gridencoder.cu:66-70) for D=3: the three strides 1, res, res^2 must all be <= size,
+        // then stride = res^3; hash iff that final stride exceeds the table (gridtype == hash)
+        v.hashed = (r > v.size || r * r > v.size || r * r * r > v.size) ? 1u : 0u;
+        lv[l] = v;
+    }
+}
+
+// entry index of grid corner (x,y,z): identical values to get_grid_index<3,C>/C
+__device__ __forceinline__ uint32_t corner_index(const LevelInfo& L, uint32_t x, uint32_t y, uint32_t z) {
+    if (L.hashed) {
+        const uint32_t h = x ^ (y * 2654435761u) ^ (z * 805459861u);
+        return L.mask ? (h & L.mask) : (h % L.size);
+    }
+    return x + y * L.res + z * L.res * L.res;      // < res^3 <= size: the reference's % size is the identity here
+}
 
 // one (sample, level) evaluation; D=3, C=2, hash grid, align_corners=False, linear (the only
 // configuration MorpheuS builds: models/model.py:144-157).  Writes feat[2]; optionally dfeat/du [3][2].
@@ -222,21 +258,20 @@ __device__ __forceinline__ void grid_eval(const GridCtx& g, uint32_t level, cons
         for (int d = 0; d < 3; d++) dfdu[d][0] = dfdu[d][1] = 0.f;
     }
     if (u[0] < 0 || u[0] > 1 || u[1] < 0 || u[1] > 1 || u[2] < 0 || u[2] > 1) return;
-    const float2* tab = reinterpret_cast<const float2*>(g.emb) + (uint32_t)g.offsets[level];
-    const uint32_t hs = g.offsets[level + 1] - g.offsets[level];
-    const uint32_t res = level_resolution(level, g.S, g.H);
+    const LevelInfo L = g.lv[level];
+    const float2* tab = reinterpret_cast<const float2*>(g.emb) + L.off;
+    const uint32_t res = L.res;
     float pos[3], dv;
-    uint32_t pg[3];
+    uint32_t pg[3], pg1[3];
 #pragma unroll
-    for (int d = 0; d < 3; d++) pos[d] = locate(u[d], res, false, 0, pg[d], dv);
+    for (int d = 0; d < 3; d++) {
+        pos[d] = locate(u[d], res, false, 0, pg[d], dv);
+        pg1[d] = min(pg[d] + 1, res - 1);
+    }
     float2 corner[8];
 #pragma unroll
-    for (uint32_t idx = 0; idx < 8; idx++) {
-        uint32_t pl[3];
-#pragma unroll
-        for (uint32_t d = 0; d < 3; d++) pl[d] = (idx & (1u << d)) ? min(pg[d] + 1, res - 1) : pg[d];
-        corner[idx] = __ldg(tab + grid_index<3>(0, hs, res, pl));
-    }
+    for (uint32_t idx = 0; idx < 8; idx++)
+        corner[idx] = __ldg(tab + corner_index(L, (idx & 1) ? pg1[0] : pg[0], (idx & 2) ? pg1[1] : pg[1], (idx & 4) ? pg1[2] : pg[2]));
 #pragma unroll
     for (uint32_t idx = 0; idx < 8; idx++) {
         float w = 1.0f;
@@ -297,25 +332,24 @@ __device__ __forceinline__ void grid_backward(const GridCtx& g, const float* __r
 #pragma unroll
         for (int d = 0; d < 3; d++) u[d] = __fdiv_rn(__fadd_rn(sp[d * P + m], g.bound), g.two_bound);
         if (u[0] < 0 || u[0] > 1 || u[1] < 0 || u[1] > 1 || u[2] < 0 || u[2] > 1) continue;
-        const uint32_t hs = g.offsets[l + 1] - g.offsets[l];
-        const uint32_t res = level_resolution(l, g.S, g.H);
-        const float2* tab = reinterpret_cast<const float2*>(g.emb) + (uint32_t)g.offsets[l];
-        float* gt = gemb + 2 * (size_t)(uint32_t)g.offsets[l];
+        const LevelInfo L = g.lv[l];
+        const uint32_t res = L.res;
+        const float2* tab = reinterpret_cast<const float2*>(g.emb) + L.off;
+        float* gt = gemb + 2 * (size_t)L.off;
         float pos[3], dv;
-        uint32_t pg[3];
+        uint32_t pg[3], pg1[3];
 #pragma unroll
-        for (int d = 0; d < 3; d++) pos[d] = locate(u[d], res, false, 0, pg[d], dv);
+        for (int d = 0; d < 3; d++) {
+            pos[d] = locate(u[d], res, false, 0, pg[d], dv);
+            pg1[d] = min(pg[d] + 1, res - 1);
+        }
         uint32_t cidx[8];
 #pragma unroll
         for (uint32_t c = 0; c < 8; c++) {
-            uint32_t pl[3];
             float w = 1.0f;
 #pragma unroll
-            for (uint32_t d = 0; d < 3; d++) {
-                pl[d] = (c & (1u << d)) ? min(pg[d] + 1, res - 1) : pg[d];
-                w = __fmul_rn(w, (c & (1u << d)) ? pos[d] : __fsub_rn(1.0f, pos[d]));
-            }
-            cidx[c] = grid_index<3>(0, hs, res, pl);
+            for (uint32_t d = 0; d < 3; d++) w = __fmul_rn(w, (c & (1u << d)) ? pos[d] : __fsub_rn(1.0f, pos[d]));
+            cidx[c] = corner_index(L, (c & 1) ? pg1[0] : pg[0], (c & 2) ? pg1[1] : pg[1], (c & 4) ? pg1[2] : pg[2]);
             red_add2(gt + 2 * cidx[c], w * g0, w * g1);
         }
         if (gp) {

@@ -93,8 +93,11 @@ __global__ void __launch_bounds__(FT, 2) field_fwd_kernel(const mb_field_params 
     const int tid = threadIdx.x;
     const float* A = p.arena;
     const uint32_t flags = io.flags;
-    const GridCtx gs{p.emb_sdf, p.offsets, p.S, p.H, p.n_levels, p.bound, p.two_bound};
-    const GridCtx gc{p.emb_col, p.offsets, p.S, p.H, p.n_levels, p.bound, p.two_bound};
+    __shared__ LevelInfo s_levels[16];
+    if (p.offsets) init_levels(s_levels, p.offsets, p.S, p.H);
+    __syncthreads();
+    const GridCtx gs{p.emb_sdf, p.offsets, p.S, p.H, p.n_levels, p.bound, p.two_bound, s_levels};
+    const GridCtx gc{p.emb_col, p.offsets, p.S, p.H, p.n_levels, p.bound, p.two_bound, s_levels};
 
     const uint32_t n_tiles = div_up(io.M, TM);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {

@@ -41,7 +41,8 @@ struct Smem {
     static constexpr int SQ = SSDF + 512;                    // [6][128]
     static constexpr int ST = SQ + 6 * 512;
     static constexpr int SALB = ST + 512;                    // [3][128]
-    static constexpr int OPS = SALB + 3 * 512;               // Op[MAX_OPS]
+    static constexpr int STQ = SALB + 3 * 512;               // [2][128] per-row topo of an FD sub-tile
+    static constexpr int OPS = STQ + 2 * 512;                // Op[MAX_OPS]
     static constexpr int BAR = OPS + MAX_OPS * 12;           // mbarriers (8-byte aligned)
     static constexpr int TMEMH = BAR + 8 * (2 * NSTAGE + 2);
     static constexpr int TOTAL = TMEMH + 16;
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
     float* sq = reinterpret_cast<float*>(smem + Smem::SQ);
     float* st = reinterpret_cast<float*>(smem + Smem::ST);
     float* salb = reinterpret_cast<float*>(smem + Smem::SALB);
+    float* stq = reinterpret_cast<float*>(smem + Smem::STQ);
     Op* ops = reinterpret_cast<Op*>(smem + Smem::OPS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BAR);
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + Smem::TMEMH);
@@ -122,6 +124,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
     // ---- op list (identical for every tile): layer index into tc_off[] = order deform[6], topo[6], sdf[3], color[3], sdf2_row0 ----
     // tc_off[3*i+0] = byte offset, [3*i+1] = nk, [3*i+2] = n_pad ; entry 18 = sdf layer 2 restricted to N=16 (FD queries)
     __shared__ int n_ops_s;
+    __shared__ LevelInfo s_levels[16];
+    if (p.offsets) init_levels(s_levels, p.offsets, p.S, p.H);
     if (tid == 0) {
         int n = 0;
         auto push = [&](int layer, int nmma) {
@@ -218,12 +222,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
         const int m = tid & (TM - 1);
         const int wg = tid >> 7;            // warpgroup 0/1
         const int warp_q = warp & 3;        // TMEM lane quarter
-        const GridCtx gs{p.emb_sdf, p.offsets, p.S, p.H, p.n_levels, p.bound, p.two_bound};
-        const GridCtx gc{p.emb_col, p.offsets, p.S, p.H, p.n_levels, p.bound, p.two_bound};
+        const GridCtx gs{p.emb_sdf, p.offsets, p.S, p.H, p.n_levels, p.bound, p.two_bound, s_levels};
+        const GridCtx gc{p.emb_col, p.offsets, p.S, p.H, p.n_levels, p.bound, p.two_bound, s_levels};
         auto bar_workers = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory"); };
 
         // SDF-net input at point pt[3]: cores 0-4 freq, 5-8 grid, 9 topo
-        auto build_sdf_input = [&](const float* pt3) {
+        auto build_sdf_input = [&](const float* pt3, const float* topo2) {
             float pnt[3] = {pt3[m], pt3[TM + m], pt3[2 * TM + m]};
             if (wg == 0) {
                 build_freq_tc(A, m, pnt, (int)p.n_freq);
@@ -232,7 +236,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
                 build_grid_core_tc(A, m, 6, gs, 4, pnt);
                 build_grid_core_tc(A, m, 7, gs, 8, pnt);
                 build_grid_core_tc(A, m, 8, gs, 12, pnt);
-                float v[8] = {stopo[m], stopo[TM + m], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                float v[8] = {topo2[m], topo2[TM + m], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 store_core(A, m, 9, v);
             }
         };
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
             bar_workers();
             // ---- main query ----
             if (flags & MB_F_MAIN) {
-                build_sdf_input(sxw);
+                build_sdf_input(sxw, stopo);
                 signal_a(c);
                 wait_acc(c);
                 epilogue_hidden<64>(c, AR + p.sdf[0].b_off, m, wg, warp_q);
@@ -351,22 +355,27 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
                 tc_fence_before();
                 bar_workers();
             }
-            // ---- finite-difference normal: 6 SDF queries ----
+            // ---- finite-difference normal: 6 SDF queries per sample, processed as 6 sub-tiles of 128 (sample, query) rows with
+            //      the query index fastest, so that the six +-eps points of a sample sit in neighbouring lanes and their
+            //      hash-grid gathers hit the same L1 sectors (same cell at all but the finest levels) ----
             if (flags & MB_F_FD) {
                 const float* pt = (flags & MB_F_FD_WARPED) ? sxw : sx;
-                for (int q = 0; q < 6; q++) {
-                    const int axis = q >> 1;
-                    const float e = (q & 1) ? -FD_EPS : FD_EPS;
+                for (int j = 0; j < 6; j++) {
                     if (tid < TM) {
+                        const int Q = j * TM + tid, s = Q / 6, q = Q - s * 6;
+                        const int axis = q >> 1;
+                        const float e = (q & 1) ? -FD_EPS : FD_EPS;
 #pragma unroll
                         for (int a = 0; a < 3; a++) {
-                            float v = pt[a * TM + tid];
+                            float v = pt[a * TM + s];
                             if (a == axis) v = __fadd_rn(v, e);
                             spt[a * TM + tid] = fminf(fmaxf(v, -p.bound), p.bound);
                         }
+                        stq[tid] = stopo[s];
+                        stq[TM + tid] = stopo[TM + s];
                     }
                     bar_workers();
-                    build_sdf_input(spt);
+                    build_sdf_input(spt, stq);
                     signal_a(c);
                     wait_acc(c);
                     epilogue_hidden<64>(c, AR + p.sdf[0].b_off, m, wg, warp_q);
@@ -378,7 +387,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
                     if (wg == 0) {
                         float v[16];
                         tmem_ld16(c.tmem + ((uint32_t)(warp_q * 32) << 16), v);
-                        sq[q * TM + m] = v[0] + __ldg(AR + p.sdf[2].b_off);
+                        const int Q = j * TM + m, s = Q / 6, q = Q - s * 6;
+                        sq[q * TM + s] = v[0] + __ldg(AR + p.sdf[2].b_off);
                     }
                     tc_fence_before();
                     bar_workers();
