@@ -173,6 +173,12 @@ int mb_field_backward(const mb_field_params* p, const mb_field_io* io, const mb_
  * mb_field_forward_tc, d/d(deform) [M,3] and d/d(topo) [M,2] (from mb_field_backward with MB_F_SKIP_WARP_BWD) and
  * accumulates weight/bias gradients into g_arena, code-line gradients into g_code, and ADDS d/dx into g_x [M,3].
  * tc_weights_t / tc_off_t: dgrad operands packed by mb_pack_tc in mode 1 (12 layers: deform[6], topo[6]). */
+/* Tensor-core backward of the SDF + colour networks, Laplace density, shading and FD-normal queries (everything of
+ * mb_field_backward except the deform/topology nets; with WARP it requires MB_F_SKIP_WARP_BWD and writes g_def_out /
+ * g_topo_out for mb_field_backward_warp_tc).  tc_weights/tc_off: forward tables of mb_field_forward_tc;
+ * tc_weights_t/tc_off_t: dgrad operands of sdf[3], color[3] (mb_pack_tc mode 1). */
+int mb_field_backward_sdf_tc(const mb_field_params* p, const mb_field_io* io, const mb_field_grads* g, const void* tc_weights,
+                             const uint32_t* tc_off, const void* tc_weights_t, const uint32_t* tc_off_t, mb_stream_t stream);
 int mb_field_backward_warp_tc(const mb_field_params* p, const float* x, const float* t, uint32_t M, const float* g_def,
                               const float* g_topo, const void* stash, const void* tc_weights_t, const uint32_t* tc_off_t,
                               float* g_arena, float* const g_code[3], float* g_x, mb_stream_t stream);

@@ -18,6 +18,8 @@ _lib = None
 USE_TC = os.environ.get('MORPHEUS_B200_TC', '1') != '0'
 # tensor-core backward of the deform/topology nets (needs the forward activation stash, i.e. USE_TC)
 USE_TC_BWD = os.environ.get('MORPHEUS_B200_TC_BWD', '1') != '0'
+# tensor-core backward of the SDF / colour nets + FD queries (recompute on tcgen05, per-tile TMEM weight-gradient accumulators)
+USE_TC_BWD_SDF = os.environ.get('MORPHEUS_B200_TC_BWD_SDF', '1') != '0'
 
 
 class LayerDesc(C.Structure):
@@ -56,7 +58,7 @@ SHADE = {'albedo': 0, 'lambertian': 1, 'albedo_normal': 1, 'textureless': 2, 'no
 SYMBOLS = ['mb_version', 'mb_last_error', 'mb_sm_count', 'mb_grid_encode_forward', 'mb_grid_encode_backward',
            'mb_sample_rays_count', 'mb_sample_rays_write', 'mb_sample_rays_uniform', 'mb_composite_forward',
            'mb_composite_backward', 'mb_field_forward', 'mb_field_backward', 'mb_occ_update', 'mb_occ_binarize',
-           'mb_adam_step', 'mb_sds_grad', 'mb_add_noise', 'mb_pack_tc', 'mb_field_forward_tc', 'mb_adam_step_dev', 'mb_field_backward_warp_tc']
+           'mb_adam_step', 'mb_sds_grad', 'mb_add_noise', 'mb_pack_tc', 'mb_field_forward_tc', 'mb_adam_step_dev', 'mb_field_backward_warp_tc', 'mb_field_backward_sdf_tc']
 
 
 def lib():

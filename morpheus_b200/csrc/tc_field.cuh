@@ -8,16 +8,16 @@ namespace tc {
 
 constexpr int A_LO_OFF = 32768;         // lo-part offset (bytes) of a 128 x 128 fp16 operand tile
 
-__device__ __forceinline__ void store_core(uint8_t* A, int m, int kc, const float (&v)[8]) {
+__device__ __forceinline__ void store_core(uint8_t* A, int m, int kc, const float (&v)[8], int lo_off = A_LO_OFF) {
     uint4 hi, lo;
     split8(v, hi, lo);
     uint8_t* p = A + kc * 2048 + (m >> 3) * 128 + (m & 7) * 16;
     *reinterpret_cast<uint4*>(p) = hi;
-    *reinterpret_cast<uint4*>(p + A_LO_OFF) = lo;
+    *reinterpret_cast<uint4*>(p + lo_off) = lo;
 }
 
 // freq encoding in the tc feature order: cores 0..4 = [p(3), sin/cos bands (36), 0]
-__device__ __forceinline__ void build_freq_tc(uint8_t* A, int m, const float p[3], int n_freq) {
+__device__ __forceinline__ void build_freq_tc(uint8_t* A, int m, const float p[3], int n_freq, int lo_off = A_LO_OFF) {
     float f[40];
     f[0] = p[0]; f[1] = p[1]; f[2] = p[2];
     float fr = 1.0f;
@@ -38,12 +38,12 @@ __device__ __forceinline__ void build_freq_tc(uint8_t* A, int m, const float p[3
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) v[i] = f[c * 8 + i];
-        store_core(A, m, c, v);
+        store_core(A, m, c, v, lo_off);
     }
 }
 
 // 4 grid levels (8 features) -> one core
-__device__ __forceinline__ void build_grid_core_tc(uint8_t* A, int m, int kc, const GridCtx& g, int level0, const float p[3]) {
+__device__ __forceinline__ void build_grid_core_tc(uint8_t* A, int m, int kc, const GridCtx& g, int level0, const float p[3], int lo_off = A_LO_OFF) {
     float u[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) u[d] = __fdiv_rn(__fadd_rn(p[d], g.bound), g.two_bound);
@@ -55,7 +55,7 @@ __device__ __forceinline__ void build_grid_core_tc(uint8_t* A, int m, int kc, co
         v[2 * j] = feat[0];
         v[2 * j + 1] = feat[1];
     }
-    store_core(A, m, kc, v);
+    store_core(A, m, kc, v, lo_off);
 }
 
 __device__ __forceinline__ float code_value(const mb_field_params& p, int v, int c, float t) {

@@ -26,6 +26,14 @@ _TC_TABLES = {}
 
 
 _TC_TABLES_T = {}
+_TC_TABLES_S = {}
+
+
+def _tc_tables_small(dev):
+    key = str(dev)
+    if key not in _TC_TABLES_S:
+        _TC_TABLES_S[key] = packing.tc_tables_dgrad_small(dev)
+    return _TC_TABLES_S[key]
 
 
 def _tc_tables_dgrad(dev):
@@ -316,8 +324,20 @@ class _FieldQuery(torch.autograd.Function):
             g_def_out = torch.empty(M, 3, device=x.device)
             g_topo_out = torch.empty(M, 2, device=x.device)
             G.g_def_out, G.g_topo_out = ptr(g_def_out), ptr(g_topo_out)
-        with _lib.timed('field_bwd_main' if flags & F_MAIN else 'field_bwd_aux'):
-            check(_lib.lib().mb_field_backward(_lib.C.byref(P), _lib.C.byref(io), _lib.C.byref(G), stream()), 'field_backward')
+        use_sdf_tc = _lib.USE_TC and _lib.USE_TC_BWD_SDF and (flags & (F_MAIN | F_FD)) and (stash is not None or not (flags & F_WARP))
+        if use_sdf_tc:
+            tabs_f = _tc_tables(x.device)
+            tabs_s = _tc_tables_small(x.device)
+            tcw_f = torch.empty(tabs_f[2], dtype=torch.uint8, device=x.device)
+            tcw_s = torch.empty(tabs_s[2], dtype=torch.uint8, device=x.device)
+            check(_lib.lib().mb_pack_tc(ptr(arena.detach()), ptr(tabs_f[0]), 18, ptr(tcw_f), stream()), 'pack_tc')
+            check(_lib.lib().mb_pack_tc(ptr(arena.detach()), ptr(tabs_s[0]), 6, ptr(tcw_s), stream()), 'pack_tc(dgrad sdf)')
+            with _lib.timed('field_bwd_sdf_tc_main' if flags & F_MAIN else 'field_bwd_sdf_tc_aux'):
+                check(_lib.lib().mb_field_backward_sdf_tc(_lib.C.byref(P), _lib.C.byref(io), _lib.C.byref(G), ptr(tcw_f), ptr(tabs_f[1]),
+                                                          ptr(tcw_s), ptr(tabs_s[1]), stream()), 'field_backward_sdf_tc')
+        else:
+            with _lib.timed('field_bwd_main' if flags & F_MAIN else 'field_bwd_aux'):
+                check(_lib.lib().mb_field_backward(_lib.C.byref(P), _lib.C.byref(io), _lib.C.byref(G), stream()), 'field_backward')
         if stash is not None:
             tabs = _tc_tables_dgrad(x.device)
             tcw_t = torch.empty(tabs[2], dtype=torch.uint8, device=x.device)

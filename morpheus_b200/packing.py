@@ -94,3 +94,17 @@ def tc_tables_dgrad(device):
             off.append([dst, Np // 16, rows])
             dst += (Np // 16) * 64 * rows
     return (torch.tensor(desc, dtype=torch.int32, device=device), torch.tensor(off, dtype=torch.int32, device=device), dst)
+
+
+def tc_tables_dgrad_small(device):
+    """dgrad B operands of the SDF and colour nets (pack mode 1): 6 layers sdf[3], color[3];
+    sdf layer 0 uses the core-aligned tc feature order (kind 2, 80 rows)."""
+    desc, off, dst = [], [], 0
+    for net in ('sdf', 'color'):
+        for li, (wt_off, w_off, b_off, K, N, Kp, Np) in enumerate(LAYOUT[net]):
+            kind = 2 if (net == 'sdf' and li == 0) else 0
+            rows = 80 if kind == 2 else Kp
+            desc.append([wt_off, K, Np, rows, kind, dst, Np, 1])
+            off.append([dst, Np // 16, rows])
+            dst += (Np // 16) * 64 * rows
+    return (torch.tensor(desc, dtype=torch.int32, device=device), torch.tensor(off, dtype=torch.int32, device=device), dst)

@@ -476,3 +476,60 @@ def test_tc_backward_matches_simt(dev):
     errs = {n: rel_l2(cpu(grads[True][n]), cpu(grads[False][n])) for n in grads[False] if float(grads[False][n].abs().max()) > 0}
     bad = {n: e for n, e in errs.items() if e > 2e-4}
     assert not bad, f'{bad}\nall: {errs}'
+
+
+@pytest.mark.parametrize('case', ['albedo_normal', 'lambertian', 'albedo', 'normal_aux', 'normal_warped', 'density'])
+def test_tc_backward_sdf_matches_simt(dev, case):
+    """tensor-core backward of the SDF / colour nets, shading and FD queries (field_bwd_sdf_tc) vs the fp32 SIMT backward,
+    for every query type the training step issues"""
+    from morpheus_b200 import _lib
+    from oracle.fields import init_reference_like_state
+    sd = init_reference_like_state(200, seed=21, randomize=True, emb_scale=0.3)
+    sd['sdf2density.beta'] = torch.tensor(0.5)
+    M = 500
+    g = torch.Generator().manual_seed(4)
+    x = ((torch.rand(M, 3, generator=g) * 2 - 1) * 0.95).to(dev)
+    t = torch.full((M, 1), 57.0 / 200, device=dev)
+    light = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1).to(dev)
+    w = [torch.randn(M, generator=g).to(dev), torch.randn(M, 3, generator=g).to(dev), torch.randn(M, 3, generator=g).to(dev),
+         torch.randn(M, generator=g).to(dev)]
+
+    def run(m, xg):
+        if case in ('albedo_normal', 'lambertian'):
+            sdf, sigma, color, normal, deform, raw = m(xg, t, light, ratio=1.0 if case == 'albedo_normal' else 0.3,
+                                                       shading='albedo_normal' if case == 'albedo_normal' else 'lambertian')
+            return (sdf * w[0]).sum() + (color * w[1]).sum() + (normal * w[2]).sum() + (sigma * w[3]).sum() * 0.05
+        if case == 'albedo':
+            sdf, sigma, color, _, deform, _ = m(xg, t, None, shading='albedo')
+            return (sdf * w[0]).sum() + (color * w[1]).sum() + (sigma * w[3]).sum() * 0.05
+        if case == 'normal_aux':
+            n, raw = m.normal(xg, topo=None)
+            return (n * w[2]).sum()
+        if case == 'normal_warped':
+            n, raw = m.normal(xg, t=t)
+            return (n * w[2]).sum()
+        d = m.density(xg, t)
+        return (d['sdf'] * w[0]).sum() + (d['albedo'] * w[1]).sum()
+
+    grads = {}
+    old = (_lib.USE_TC, _lib.USE_TC_BWD, _lib.USE_TC_BWD_SDF)
+    try:
+        for tc in (False, True):
+            _lib.USE_TC, _lib.USE_TC_BWD, _lib.USE_TC_BWD_SDF = True, tc, tc
+            _lib.PROFILE.reset()
+            _lib.PROFILE.enabled = True
+            m = make_model(sd, 0.9, dev).train()
+            xg = x.clone().requires_grad_(True)
+            run(m, xg).backward()
+            torch.cuda.synchronize()
+            launched = set(_lib.PROFILE.summary())
+            assert any(k.startswith('field_bwd_sdf_tc') for k in launched) == tc, launched
+            grads[tc] = {'x': xg.grad.clone(), **{n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}}
+    finally:
+        _lib.USE_TC, _lib.USE_TC_BWD, _lib.USE_TC_BWD_SDF = old
+        _lib.PROFILE.enabled = False
+    errs = {n: rel_l2(cpu(grads[True][n]), cpu(grads[False][n])) for n in grads[False] if float(grads[False][n].abs().max()) > 0}
+    if case in ('normal_aux', 'normal_warped'):
+        errs.pop('sdf_net.net.2.bias', None)   # the last-layer bias cancels exactly in the +-eps differences: its gradient is pure round-off
+    bad = {n: e for n, e in errs.items() if e > 3e-4}
+    assert not bad, f'{bad}\nall: {errs}'
