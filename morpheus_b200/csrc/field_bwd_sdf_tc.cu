@@ -24,7 +24,7 @@ using namespace mb::tc;
 
 constexpr int TM = 128;
 constexpr int NWORK = 256;
-constexpr int NTHREADS = NWORK + 32;
+constexpr int NTHREADS = NWORK + 64;    // + MMA-issue warp + weight-loader warp
 constexpr int NSTAGE = 3;
 constexpr int STAGE_BYTES = 5120;
 constexpr int S0_LO = 20480;        // lo offset of the 80-column S0 tile
@@ -39,6 +39,8 @@ struct OpS {
     uint8_t wlayer;   // weight-table row (forward table: 0..5 = sdf0..2, col0..2; dgrad table: same order)
     uint8_t wn;       // backward: wgrad N (dZ columns used: 64, 48 or 16)
     uint16_t wcol;    // backward: TMEM column of the wgrad accumulator
+    uint32_t src_off; // byte offset of the layer's K=16 weight slabs in the forward (kind 0) / dgrad (kind 1) table
+    uint32_t rows;    // rows of one slab (N_pad forward, R dgrad): slab bytes = 64 * rows
 };
 
 struct Smem {
@@ -65,13 +67,13 @@ struct Smem {
     static constexpr int CS = GSD + 512;                 // [1]  column sums
     static constexpr int MISC = CS + 512;                // 16 floats
     static constexpr int OPS = MISC + 64;                // OpS[MAX_OPS]
-    static constexpr int BAR = OPS + MAX_OPS * 8;        // full[3], empty[3], acc_ready, z_ready
+    static constexpr int BAR = OPS + MAX_OPS * 16;       // full[3], empty[3], acc_ready, z_ready
     static constexpr int TMEMH = BAR + 8 * (2 * NSTAGE + 2);
     static constexpr int TOTAL = TMEMH + 16;
 };
 static_assert(Smem::BAR % 8 == 0 && Smem::OPS % 8 == 0, "alignment");
 static_assert(Smem::TOTAL <= 232448, "shared memory budget");
-static_assert(sizeof(OpS) == 8, "OpS layout");
+static_assert(sizeof(OpS) == 16, "OpS layout");
 
 __device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -136,8 +138,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
     if (p.offsets) init_levels(s_levels, p.offsets, p.S, p.H);
     if (tid == 0) {
         int n = 0;
-        auto fwd = [&](int a_tile, int nk, int nn, int wl) { ops[n] = OpS{0, (uint8_t)a_tile, (uint8_t)nk, (uint8_t)nn, (uint8_t)wl, 0, 0}; n++; };
-        auto bwd = [&](int act_tile, int nk, int rows, int wl, int wn, int wcol) { ops[n] = OpS{1, (uint8_t)act_tile, (uint8_t)nk, (uint8_t)rows, (uint8_t)wl, (uint8_t)wn, (uint16_t)wcol}; n++; };
+        auto fwd = [&](int a_tile, int nk, int nn, int wl) { ops[n] = OpS{0, (uint8_t)a_tile, (uint8_t)nk, (uint8_t)nn, (uint8_t)wl, 0, 0, off_f[3 * (12 + wl)], off_f[3 * (12 + wl) + 2]}; n++; };
+        auto bwd = [&](int act_tile, int nk, int rows, int wl, int wn, int wcol) { ops[n] = OpS{1, (uint8_t)act_tile, (uint8_t)nk, (uint8_t)rows, (uint8_t)wl, (uint8_t)wn, (uint16_t)wcol, off_d[3 * wl], (uint32_t)rows}; n++; };
         if (do_main) {
             fwd(0, 5, 64, 0); fwd(1, 4, 64, 1); fwd(2, 4, 48, 2);             // S0 -> X0 -> X1 -> h
             if (do_color) { fwd(1, 4, 64, 3); fwd(2, 4, 64, 4); fwd(3, 4, 16, 5); }   // C0 = X0 -> X1 -> X2 -> rgb
@@ -165,37 +167,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
     const uint32_t n_tiles = div_up(io.M, TM);
     const uint32_t my_tiles = (blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    if (warp == NWORK / 32) {
-        // ================================ control thread ================================
+    if (warp == NWORK / 32 + 1) {
+        // ================================ weight loader thread ================================
         if (lane == 0 && my_tiles > 0 && n_ops > 0) {
             const uint64_t total_ops = (uint64_t)my_tiles * n_ops;
-            uint64_t l_op = 0; uint32_t l_step = 0;
-            uint32_t loads = 0, uses = 0, z_count = 0;
-            auto op_slabs = [&](const OpS& o, const uint8_t*& base, uint32_t& bytes) {
-                if (o.kind == 0) { base = tcw_f + off_f[3 * (12 + o.wlayer)]; bytes = 64u * off_f[3 * (12 + o.wlayer) + 2]; }
-                else { base = tcw_d + off_d[3 * o.wlayer]; bytes = 64u * o.n; }
-            };
-            auto top_up = [&]() {
-                while (loads + 1 < uses + NSTAGE && l_op < total_ops) {
-                    const OpS o = ops[l_op % n_ops];
-                    const uint8_t* base; uint32_t bytes;
-                    op_slabs(o, base, bytes);
+            uint32_t loads = 0;
+            for (uint64_t u = 0; u < total_ops; u++) {
+                const OpS o = ops[u % n_ops];
+                const uint8_t* src = (o.kind == 0 ? tcw_f : tcw_d) + o.src_off;
+                const uint32_t bytes = 64u * o.rows;
+                for (uint32_t st = 0; st < o.nk; st++) {
                     const uint32_t stg = loads % NSTAGE;
                     if (loads >= NSTAGE) mbar_wait(empty + stg, ((loads / NSTAGE) - 1) & 1);
                     mbar_arrive_expect_tx(full + stg, bytes);
-                    bulk_g2s(smem + Smem::W + stg * STAGE_BYTES, base + (size_t)l_step * bytes, bytes, full + stg);
+                    bulk_g2s(smem + Smem::W + stg * STAGE_BYTES, src + (size_t)st * bytes, bytes, full + stg);
                     loads++;
-                    if (++l_step == o.nk) { l_step = 0; l_op++; }
                 }
-            };
+            }
+        }
+    } else if (warp == NWORK / 32) {
+        // ================================ MMA-issue thread ================================
+        if (lane == 0 && my_tiles > 0 && n_ops > 0) {
+            const uint64_t total_ops = (uint64_t)my_tiles * n_ops;
+            uint32_t uses = 0, z_count = 0;
             const uint32_t sm_base = smem_u32(smem);
             const uint32_t dz_base = sm_base + Smem::DZ;
+            const uint64_t zw_hi0 = make_smem_desc(dz_base, 128, 2048), zw_lo0 = make_smem_desc(dz_base + X_LO, 128, 2048);   // dZ as MN-major wgrad B
             uint32_t used_mask = 0;          // wgrad accumulators already written in this tile (bit = (wcol-128)/64)
             for (uint64_t u = 0; u < total_ops; u++) {
                 const uint32_t oi = (uint32_t)(u % n_ops);
                 if (oi == 0) used_mask = 0;
                 const OpS o = ops[oi];
-                top_up();
                 mbar_wait(z_ready, z_count & 1);
                 z_count++;
                 tc_fence_after();
@@ -206,11 +208,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
                     const uint32_t bit = 1u << ((o.wcol - 128) / 64);
                     const bool first = !(used_mask & bit);
                     used_mask |= bit;
+                    const uint64_t a_hi0 = make_smem_desc(a_base, 128, 2048), a_lo0 = make_smem_desc(a_base + a_lo, 128, 2048);
+#pragma unroll
                     for (uint32_t s = 0; s < 8; s++) {
-                        const uint64_t a_hi = make_smem_desc(a_base + s * 256, 128, 2048);
-                        const uint64_t a_lod = make_smem_desc(a_base + a_lo + s * 256, 128, 2048);
-                        const uint64_t b_hi = make_smem_desc(dz_base + s * 256, 128, 2048);
-                        const uint64_t b_lo = make_smem_desc(dz_base + X_LO + s * 256, 128, 2048);
+                        const uint64_t a_hi = a_hi0 + s * 16, a_lod = a_lo0 + s * 16;        // + 256 B per K step (MN-major)
+                        const uint64_t b_hi = zw_hi0 + s * 16, b_lo = zw_lo0 + s * 16;
                         umma_f16(tmem + o.wcol, a_hi, b_hi, idesc, (first && s == 0) ? 0u : 1u);
                         umma_f16(tmem + o.wcol, a_hi, b_lo, idesc, 1u);
                         umma_f16(tmem + o.wcol, a_lod, b_hi, idesc, 1u);
@@ -220,23 +222,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
                     // ---- forward GEMM (A = activation tile) or dgrad (A = dZ tile); B = weight slabs from the ring ----
                     const uint32_t a_base = (o.kind == 0) ? sm_base + tile_base(o.a_tile) : dz_base;
                     const uint32_t a_lo = (o.kind == 0) ? tile_lo(o.a_tile) : (uint32_t)X_LO;
-                    const uint32_t rows = (o.kind == 0) ? off_f[3 * (12 + o.wlayer) + 2] : (uint32_t)o.n;    // rows of the slab (N_pad or R)
+                    const uint32_t rows = o.rows;                                            // rows of the slab (N_pad or R)
                     const uint32_t idesc = make_idesc_f16(o.n);
+                    const uint64_t a_hi0 = make_smem_desc(a_base, 2048, 128), a_lo0 = make_smem_desc(a_base + a_lo, 2048, 128);
+                    const uint64_t b_op = make_smem_desc(sm_base + Smem::W, 16u * rows, 128);
+                    const uint64_t b_lo_add = (32u * rows) >> 4;
                     for (uint32_t s = 0; s < o.nk; s++) {
                         const uint32_t stg = uses % NSTAGE;
                         mbar_wait(full + stg, (uses / NSTAGE) & 1);
                         tc_fence_after();
-                        const uint32_t wb = sm_base + Smem::W + stg * STAGE_BYTES;
-                        const uint64_t a_hi = make_smem_desc(a_base + s * 4096, 2048, 128);
-                        const uint64_t a_lod = make_smem_desc(a_base + a_lo + s * 4096, 2048, 128);
-                        const uint64_t b_hi = make_smem_desc(wb, 16u * rows, 128);
-                        const uint64_t b_lo = make_smem_desc(wb + 32u * rows, 16u * rows, 128);
+                        const uint64_t a_hi = a_hi0 + (uint64_t)s * 256, a_lod = a_lo0 + (uint64_t)s * 256;    // + 4096 B per K step
+                        const uint64_t b_hi = b_op + (uint64_t)stg * (STAGE_BYTES >> 4), b_lo = b_hi + b_lo_add;
                         umma_f16(tmem, a_hi, b_hi, idesc, s > 0 ? 1u : 0u);
                         umma_f16(tmem, a_hi, b_lo, idesc, 1u);
                         umma_f16(tmem, a_lod, b_hi, idesc, 1u);
                         umma_commit(empty + stg);
                         uses++;
-                        top_up();
                     }
                 }
                 umma_commit(acc_ready);

@@ -20,7 +20,7 @@ using namespace mb::tc;
 
 constexpr int TM = 128;
 constexpr int NWORK = 256;
-constexpr int NTHREADS = NWORK + 32;
+constexpr int NTHREADS = NWORK + 64;    // + MMA-issue warp + weight-loader warp
 constexpr int NSTAGE = 3;
 constexpr int STAGE_BYTES = 8192;
 constexpr int TILE_BYTES = 65536;
@@ -104,31 +104,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_warp_tc_kernel(const mb
     const uint32_t my_tiles = (blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     // per layer (index net*6 + l) of the dgrad weight table: tc_off[3*i] = byte offset, [3*i+1] = number of K=16 slabs (N_pad/16), [3*i+2] = rows R (128 or 96)
-    if (warp == NWORK / 32) {
-        // ======================================= control thread =======================================
+    if (warp == NWORK / 32 + 1) {
+        // ======================================= weight loader thread =======================================
         if (lane == 0 && my_tiles > 0) {
-            const uint64_t total_units = (uint64_t)my_tiles * 12;     // (tile, net, layer) units in processing order
-            uint64_t l_unit = 0; uint32_t l_step = 0;                 // weight loader cursor
-            uint32_t loads = 0, uses = 0, z_count = 0, acc_count = 0, sa_count[2] = {0, 0};
-            auto unit_layer = [&](uint64_t u) { const uint32_t r = (uint32_t)(u % 12); return (r / 6) * 6 + (5 - r % 6); };  // -> net*6 + l
-            auto top_up = [&]() {
-                while (loads + 1 < uses + NSTAGE && l_unit < total_units) {
-                    const uint32_t li = unit_layer(l_unit);
+            uint32_t loads = 0;
+            for (uint32_t it = 0; it < my_tiles; it++)
+                for (uint32_t r = 0; r < 12; r++) {                   // (net, layer) units in processing order
+                    const uint32_t li = (r / 6) * 6 + (5 - r % 6);
                     const uint32_t nk = tc_off[3 * li + 1], R = tc_off[3 * li + 2];
-                    const uint32_t stg = loads % NSTAGE;
-                    if (loads >= NSTAGE) mbar_wait(empty + stg, ((loads / NSTAGE) - 1) & 1);
                     const uint32_t bytes = 64u * R;
-                    mbar_arrive_expect_tx(full + stg, bytes);
-                    bulk_g2s(smem + Smem::W + stg * STAGE_BYTES, tcw + tc_off[3 * li] + (size_t)l_step * bytes, bytes, full + stg);
-                    loads++;
-                    if (++l_step == nk) { l_step = 0; l_unit++; }
+                    const uint8_t* src = tcw + tc_off[3 * li];
+                    for (uint32_t st = 0; st < nk; st++) {
+                        const uint32_t stg = loads % NSTAGE;
+                        if (loads >= NSTAGE) mbar_wait(empty + stg, ((loads / NSTAGE) - 1) & 1);
+                        mbar_arrive_expect_tx(full + stg, bytes);
+                        bulk_g2s(smem + Smem::W + stg * STAGE_BYTES, src + (size_t)st * bytes, bytes, full + stg);
+                        loads++;
+                    }
                 }
-            };
+        }
+    } else if (warp == NWORK / 32) {
+        // ======================================= MMA-issue thread =======================================
+        if (lane == 0 && my_tiles > 0) {
+            uint32_t uses = 0, z_count = 0, acc_count = 0, sa_count[2] = {0, 0};
             auto load_tile = [&](uint64_t tile, uint32_t net, uint32_t l, uint32_t buf) {   // A_l (l >= 1) = stash slot l-1
                 mbar_arrive_expect_tx(sa_full + buf, TILE_BYTES);
                 bulk_g2s(smem + (buf ? Smem::SA1 : Smem::SA0), stash + (tile * 10 + net * 5 + (l - 1)) * (uint64_t)TILE_BYTES, TILE_BYTES, sa_full + buf);
             };
             const uint32_t sz_base = smem_u32(smem + Smem::SZ);
+            const uint32_t w_base = smem_u32(smem + Smem::W);
+            // dZ tile as the MN-major B operand of wgrad (zw) and as the K-major A operand of dgrad (zd)
+            const uint64_t zw_hi0 = make_smem_desc(sz_base, 128, 2048), zw_lo0 = make_smem_desc(sz_base + A_LO_OFF, 128, 2048);
+            const uint64_t zd_hi0 = make_smem_desc(sz_base, 2048, 128), zd_lo0 = make_smem_desc(sz_base + A_LO_OFF, 2048, 128);
             for (uint32_t it = 0; it < my_tiles; it++) {
                 const uint64_t tile = blockIdx.x + (uint64_t)it * gridDim.x;
                 for (uint32_t net = 0; net < 2; net++) {
@@ -140,7 +147,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_warp_tc_kernel(const mb
                     for (int l = 5; l >= 0; l--) {
                         const uint32_t buf = (5 - l) & 1;
                         const uint32_t li = net * 6 + l;
-                        top_up();
                         mbar_wait(z_ready, z_count & 1);
                         z_count++;
                         tc_fence_after();
@@ -152,11 +158,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_warp_tc_kernel(const mb
                         // ---- wgrad: D_w[k][n] (TMEM cols 128..) ----
                         {
                             const uint32_t idesc = make_idesc_f16_mn(n_l);
+                            const uint64_t a_hi0 = make_smem_desc(sa_base, 128, 2048), a_lo0 = make_smem_desc(sa_base + A_LO_OFF, 128, 2048);
+#pragma unroll
                             for (uint32_t s = 0; s < 8; s++) {
-                                const uint64_t a_hi = make_smem_desc(sa_base + s * 256, 128, 2048);
-                                const uint64_t a_lo = make_smem_desc(sa_base + A_LO_OFF + s * 256, 128, 2048);
-                                const uint64_t b_hi = make_smem_desc(sz_base + s * 256, 128, 2048);
-                                const uint64_t b_lo = make_smem_desc(sz_base + A_LO_OFF + s * 256, 128, 2048);
+                                const uint64_t a_hi = a_hi0 + s * 16, a_lo = a_lo0 + s * 16;          // + 256 B per K step (MN-major)
+                                const uint64_t b_hi = zw_hi0 + s * 16, b_lo = zw_lo0 + s * 16;
                                 umma_f16(tmem + 128, a_hi, b_hi, idesc, s > 0 ? 1u : 0u);
                                 umma_f16(tmem + 128, a_hi, b_lo, idesc, 1u);
                                 umma_f16(tmem + 128, a_lo, b_hi, idesc, 1u);
@@ -166,21 +172,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_warp_tc_kernel(const mb
                         {
                             const uint32_t nk = tc_off[3 * li + 1], R = tc_off[3 * li + 2];
                             const uint32_t idesc = make_idesc_f16(R);
+                            const uint64_t b_op = make_smem_desc(w_base, 16u * R, 128);
+                            const uint64_t b_lo_add = (32u * R) >> 4;
                             for (uint32_t s = 0; s < nk; s++) {
                                 const uint32_t stg = uses % NSTAGE;
                                 mbar_wait(full + stg, (uses / NSTAGE) & 1);
                                 tc_fence_after();
-                                const uint32_t wb = smem_u32(smem + Smem::W + stg * STAGE_BYTES);
-                                const uint64_t a_hi = make_smem_desc(sz_base + s * 4096, 2048, 128);
-                                const uint64_t a_lo = make_smem_desc(sz_base + A_LO_OFF + s * 4096, 2048, 128);
-                                const uint64_t b_hi = make_smem_desc(wb, 16u * R, 128);
-                                const uint64_t b_lo = make_smem_desc(wb + 32u * R, 16u * R, 128);
+                                const uint64_t a_hi = zd_hi0 + (uint64_t)s * 256, a_lo = zd_lo0 + (uint64_t)s * 256;   // + 4096 B per K step
+                                const uint64_t b_hi = b_op + (uint64_t)stg * (STAGE_BYTES >> 4), b_lo = b_hi + b_lo_add;
                                 umma_f16(tmem, a_hi, b_hi, idesc, s > 0 ? 1u : 0u);
                                 umma_f16(tmem, a_hi, b_lo, idesc, 1u);
                                 umma_f16(tmem, a_lo, b_hi, idesc, 1u);
                                 umma_commit(empty + stg);
                                 uses++;
-                                top_up();
                             }
                         }
                         umma_commit(acc_ready);

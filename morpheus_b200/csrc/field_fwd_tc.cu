@@ -21,7 +21,7 @@ namespace tc {
 
 constexpr int TM = 128;                 // samples per tile
 constexpr int NWORK = 256;              // worker threads (8 warps)
-constexpr int NTHREADS = NWORK + 32;    // + control warp
+constexpr int NTHREADS = NWORK + 64;    // + MMA-issue warp + weight-loader warp
 constexpr int NSTAGE = 4;
 constexpr int STAGE_BYTES = 8192;       // one K=16 slab of a 128-wide layer: (hi + lo) * 2 cores * 128 rows * 16 B
 constexpr int MAX_OPS = 40;
@@ -161,28 +161,38 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
     const uint32_t n_tiles = div_up(io.M, TM);
     const uint32_t my_tiles = (blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    if (warp == NWORK / 32) {
-        // =============================== control warp: weight stream + MMA issue ===============================
+    if (warp == NWORK / 32 + 1) {
+        // =============================== loader warp: weight slabs -> ring (one bulk copy per K=16 slab) ===============================
         if (lane == 0 && my_tiles > 0 && n_ops > 0) {
             const uint64_t total_ops = (uint64_t)my_tiles * n_ops;
-            uint64_t l_op = 0; uint32_t l_step = 0;          // loader cursor
-            uint32_t loads = 0, uses = 0, a_count = 0;
-            auto top_up = [&]() {
-                while (loads + 1 < uses + NSTAGE && l_op < total_ops) {
-                    const Op& o = ops[l_op % n_ops];
+            uint32_t loads = 0;
+            for (uint64_t u = 0; u < total_ops; u++) {
+                const Op o = ops[u % n_ops];
+                const uint32_t bytes = 64u * o.n_pad;     // (hi + lo) * 2 cores * n_pad rows * 16 B
+                for (uint32_t st = 0; st < o.nk; st++) {
                     const uint32_t stg = loads % NSTAGE;
                     if (loads >= NSTAGE) mbar_wait(c.empty + stg, ((loads / NSTAGE) - 1) & 1);
-                    const uint32_t bytes = 64u * o.n_pad;     // (hi + lo) * 2 cores * n_pad rows * 16 B
                     mbar_arrive_expect_tx(c.full + stg, bytes);
-                    bulk_g2s(smem + Smem::W + stg * STAGE_BYTES, tcw + o.src_off + (size_t)l_step * bytes, bytes, c.full + stg);
+                    bulk_g2s(smem + Smem::W + stg * STAGE_BYTES, tcw + o.src_off + (size_t)st * bytes, bytes, c.full + stg);
                     loads++;
-                    if (++l_step == o.nk) { l_step = 0; l_op++; }
                 }
-            };
+            }
+        }
+    } else if (warp == NWORK / 32) {
+        // =============================== MMA-issue warp ===============================
+        if (lane == 0 && my_tiles > 0 && n_ops > 0) {
+            const uint64_t total_ops = (uint64_t)my_tiles * n_ops;
+            uint32_t uses = 0, a_count = 0;
             const uint32_t a_base = smem_u32(A);
+            const uint32_t w_base = smem_u32(smem + Smem::W);
+            const uint64_t a_hi0 = make_smem_desc(a_base, 2048, 128);
+            const uint64_t a_lo0 = make_smem_desc(a_base + A_LO_OFF, 2048, 128);
             for (uint64_t u_op = 0; u_op < total_ops; u_op++) {
                 const Op o = ops[u_op % n_ops];
-                top_up();
+                // descriptors: per op the ring-stage bases (LBO depends on the layer width); per K step only the start address moves
+                const uint64_t b_op = make_smem_desc(w_base, 16u * o.n_pad, 128);
+                const uint64_t b_lo_add = (32u * o.n_pad) >> 4;
+                const uint32_t idesc = make_idesc_f16(o.n);
                 mbar_wait(c.a_ready, a_count & 1);
                 a_count++;
                 tc_fence_after();
@@ -195,23 +205,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
                     const uint32_t slot = (op_in_tile / 6) * 5 + (op_in_tile % 6) - 1;
                     bulk_s2g(stash + (tile * 10 + slot) * 65536ull, A, 65536);
                 }
-                const uint32_t idesc = make_idesc_f16(o.n);
-                const uint32_t lbo_b = 16u * o.n_pad;
                 for (uint32_t s = 0; s < o.nk; s++) {
                     const uint32_t stg = uses % NSTAGE;
                     mbar_wait(c.full + stg, (uses / NSTAGE) & 1);
                     tc_fence_after();
-                    const uint32_t wb = smem_u32(smem + Smem::W + stg * STAGE_BYTES);
-                    const uint64_t a_hi = make_smem_desc(a_base + s * 4096, 2048, 128);
-                    const uint64_t a_lo = make_smem_desc(a_base + A_LO_OFF + s * 4096, 2048, 128);
-                    const uint64_t b_hi = make_smem_desc(wb, lbo_b, 128);
-                    const uint64_t b_lo = make_smem_desc(wb + 32u * o.n_pad, lbo_b, 128);
+                    const uint64_t a_hi = a_hi0 + (uint64_t)s * 256, a_lo = a_lo0 + (uint64_t)s * 256;     // + 4096 B per K step
+                    const uint64_t b_hi = b_op + (uint64_t)stg * (STAGE_BYTES >> 4), b_lo = b_hi + b_lo_add;
                     umma_f16(c.tmem, a_hi, b_hi, idesc, s > 0 ? 1u : 0u);
                     umma_f16(c.tmem, a_hi, b_lo, idesc, 1u);
                     umma_f16(c.tmem, a_lo, b_hi, idesc, 1u);
                     umma_commit(c.empty + stg);
                     uses++;
-                    top_up();
                 }
                 if (do_stash) bulk_store_wait_read();     // the epilogue of this op overwrites A
                 umma_commit(c.acc_ready);
