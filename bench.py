@@ -255,15 +255,18 @@ def main():
         M_local = n_local * N_SAMPLES
         sdf_fd = 73 * 64 + 64 * 64 + 64           # an FD query only needs output row 0 of the last SDF layer
         tc_bwd = 'field_bwd_warp_tc' in kern
+        sdf_bwd_main = 4 * (MAC_COLOR + MAC_SDF + 6 * sdf_fd) * M_local
         flops = {
             'field_fwd_main': 2 * (MAC_DEFORM + MAC_TOPO + MAC_COLOR + MAC_SDF + 6 * sdf_fd) * M_local,
             'field_fwd_aux': 2 * 6 * sdf_fd * M_local,
-            'field_bwd_main': 4 * ((0 if tc_bwd else MAC_DEFORM + MAC_TOPO) + MAC_COLOR + MAC_SDF + 6 * sdf_fd) * M_local,
+            'field_bwd_main': (0 if tc_bwd else 4 * (MAC_DEFORM + MAC_TOPO) * M_local) + sdf_bwd_main,
             'field_bwd_aux': 4 * 6 * sdf_fd * M_local,
+            'field_bwd_sdf_tc_main': sdf_bwd_main,
+            'field_bwd_sdf_tc_aux': 4 * 6 * sdf_fd * M_local,
             'field_bwd_warp_tc': 4 * (MAC_DEFORM + MAC_TOPO) * M_local,
         }
-        engine = {'field_fwd_main': 'tcgen05 (3x fp16 split)', 'field_fwd_aux': 'tcgen05 (3x fp16 split)', 'field_bwd_warp_tc': 'tcgen05 (3x fp16 split)',
-                  'field_bwd_main': 'fp32 SIMT', 'field_bwd_aux': 'fp32 SIMT'}
+        engine = {k: 'tcgen05 (3x fp16 split)' for k in flops}
+        engine['field_bwd_main'] = engine['field_bwd_aux'] = 'fp32 SIMT'
         rooflines = []
         for name, fl in flops.items():
             if name in kern:

@@ -23,7 +23,7 @@ namespace tcs {
 using namespace mb::tc;
 
 constexpr int TM = 128;
-constexpr int NWORK = 256;
+constexpr int NWORK = 512;              // 16 worker warps
 constexpr int NTHREADS = NWORK + 64;    // + MMA-issue warp + weight-loader warp
 constexpr int NSTAGE = 3;
 constexpr int STAGE_BYTES = 5120;
@@ -91,8 +91,108 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
     }
     return v[0];
 }
+// column sums of a [32 lanes][16] register tile: afterwards lane L holds the sum of column (L & 15) over the 16 lanes that
+// share its bit 4 (the two half-warps hold partial sums of the same column)
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int half = 8; half >= 1; half >>= 1) {
+        const bool upper = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; i++) {
+            const float send = upper ? v[i] : v[i + half];
+            const float keep = upper ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
 __device__ __forceinline__ uint32_t tile_base(int t) { return t == 0 ? Smem::S0 : Smem::X + (t - 1) * 32768; }
 __device__ __forceinline__ uint32_t tile_lo(int t) { return t == 0 ? S0_LO : X_LO; }
+
+// grid backward from G[32][128] (feature gradients of the row-wise points pt3, row r <-> query index qbase + r):
+// work item = (level, run of <= 6 consecutive rows aligned to multiples of 6 in query space, i.e. the +-eps queries of
+// ONE sample in an FD sub-tile, 6 neighbouring samples of a ray in the main sub-tile).  Rows of a run that fall into
+// the same grid cell are merged in registers, so the table scatter costs one red.v2 per corner per CELL instead of
+// per row (the scatter is LSU-throughput bound).  d/d(point) by corner differencing as kernel_input_backward.
+__device__ __noinline__ void grid_bwd_runs(const GridCtx g, const float* __restrict__ pt3, const float* __restrict__ G, float* __restrict__ gemb,
+                                    float* __restrict__ gp, float inv_scale, int qbase, int tid) {
+    const int run0 = qbase / 6;
+    const int nruns = (qbase + TM - 1) / 6 - run0 + 1;
+    const int items = (int)min(g.n_levels, 16u) * nruns;
+    for (int it = tid; it < items; it += NWORK) {
+        const int l = it / nruns, rr = it - l * nruns;
+        const int q0 = max((run0 + rr) * 6, qbase), q1 = min((run0 + rr) * 6 + 6, qbase + TM);
+        const LevelInfo L = g.lv[l];
+        const uint32_t res = L.res;
+        const float scale = (float)res;
+        const float2* tab = reinterpret_cast<const float2*>(g.emb) + L.off;
+        float* gt = gemb + 2 * (size_t)L.off;
+        bool have = false;
+        uint32_t c0 = 0, c1 = 0, c2 = 0;
+        uint32_t cidx[8];
+        float2 cv[8];
+        float acc[16];
+#pragma unroll 1
+        for (int q = q0; q < q1; q++) {
+            const int r = q - qbase;
+            const float g0 = G[(2 * l) * TM + r] * inv_scale, g1 = G[(2 * l + 1) * TM + r] * inv_scale;
+            if (g0 == 0.f && g1 == 0.f) continue;
+            float u[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) u[d] = __fdiv_rn(__fadd_rn(pt3[d * TM + r], g.bound), g.two_bound);
+            if (u[0] < 0 || u[0] > 1 || u[1] < 0 || u[1] > 1 || u[2] < 0 || u[2] > 1) continue;
+            float pos[3], dv;
+            uint32_t pg[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) pos[d] = locate(u[d], res, false, 0, pg[d], dv);
+            if (!have || pg[0] != c0 || pg[1] != c1 || pg[2] != c2) {
+                if (have) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) red_add2(gt + 2 * cidx[c], acc[2 * c], acc[2 * c + 1]);
+                }
+                have = true;
+                c0 = pg[0]; c1 = pg[1]; c2 = pg[2];
+                const uint32_t p1[3] = {min(pg[0] + 1, res - 1), min(pg[1] + 1, res - 1), min(pg[2] + 1, res - 1)};
+#pragma unroll
+                for (uint32_t c = 0; c < 8; c++) {
+                    cidx[c] = corner_index(L, (c & 1) ? p1[0] : pg[0], (c & 2) ? p1[1] : pg[1], (c & 4) ? p1[2] : pg[2]);
+                    cv[c] = __ldg(tab + cidx[c]);
+                    acc[2 * c] = acc[2 * c + 1] = 0.f;
+                }
+            }
+#pragma unroll
+            for (uint32_t c = 0; c < 8; c++) {
+                float w = 1.0f;
+#pragma unroll
+                for (uint32_t d = 0; d < 3; d++) w = __fmul_rn(w, (c & (1u << d)) ? pos[d] : __fsub_rn(1.0f, pos[d]));
+                acc[2 * c] = __fmaf_rn(w, g0, acc[2 * c]);
+                acc[2 * c + 1] = __fmaf_rn(w, g1, acc[2 * c + 1]);
+            }
+#pragma unroll
+            for (uint32_t gd = 0; gd < 3; gd++) {
+                float a = 0.f;
+#pragma unroll
+                for (uint32_t i4 = 0; i4 < 4; i4++) {
+                    float w = scale;
+                    uint32_t cl = 0;
+#pragma unroll
+                    for (uint32_t nd = 0; nd < 2; nd++) {
+                        const uint32_t d = (nd >= gd) ? nd + 1 : nd;
+                        if (i4 & (1u << nd)) { w *= pos[d]; cl |= (1u << d); }
+                        else w *= (1.0f - pos[d]);
+                    }
+                    const float2 lo = cv[cl], hi = cv[cl | (1u << gd)];
+                    a += w * ((hi.x - lo.x) * g0 + (hi.y - lo.y) * g1);
+                }
+                atomicAdd(gp + gd * TM + r, a / g.two_bound);
+            }
+        }
+        if (have) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) red_add2(gt + 2 * cidx[c], acc[2 * c], acc[2 * c + 1]);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_field_params p, const mb_field_io io, const mb_field_grads gr,
                                                                       const uint8_t* __restrict__ tcw_f, const uint32_t* __restrict__ off_f,
@@ -245,8 +345,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
         }
     } else {
         // ================================ workers ================================
+        // 512 threads: row m = tid & 127 of the 128-row tile, part = tid >> 7 in 0..3 (column / level quarter of every phase)
         const int m = tid & (TM - 1);
-        const int wg = tid >> 7;
+        const int part = tid >> 7;
         const int warp_q = warp & 3;
         const uint32_t lane_base = (uint32_t)(warp_q * 32) << 16;
         uint32_t acc_count = 0;
@@ -261,27 +362,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
         auto signal_z = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(z_ready); };
         auto wait_acc = [&]() { mbar_wait(acc_ready, acc_count & 1); acc_count++; tc_fence_after(); };
 
-        // S0 operand (80 columns) at the row-wise points pt3 with row-wise topo
+        // S0 operand (80 columns) at the row-wise points pt3 with row-wise topo: every part gathers 4 grid levels (one core),
+        // parts 0..2 build the frequency features of one axis, part 3 the pad / topo columns
         auto build_s0 = [&](const float* pt3, const float* topo2) {
             const float pnt[3] = {pt3[m], pt3[TM + m], pt3[2 * TM + m]};
-            if (wg == 0) {
-                build_freq_tc(S0, m, pnt, (int)p.n_freq, S0_LO);
-                build_grid_core_tc(S0, m, 5, gs, 0, pnt, S0_LO);
+            gather_levels_tc(S0, m, 40, gs, 4 * part, 4, pnt, S0_LO);
+            if (part < 3) {
+                freq_axis_tc(S0, m, part, pt3[part * TM + m], (int)p.n_freq, S0_LO);
             } else {
-                build_grid_core_tc(S0, m, 6, gs, 4, pnt, S0_LO);
-                build_grid_core_tc(S0, m, 7, gs, 8, pnt, S0_LO);
-                build_grid_core_tc(S0, m, 8, gs, 12, pnt, S0_LO);
+                store_one(S0, m, 39, 0.f, S0_LO);
                 const float v[8] = {topo2[m], topo2[TM + m], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 store_core(S0, m, 9, v, S0_LO);
             }
         };
-        // hidden forward epilogue: relu(acc + bias) -> 64-column tile dst (each warpgroup 32 columns)
+        // hidden forward epilogue: relu(acc + bias) -> 64-column tile dst (16 columns per part)
         auto ep_hidden = [&](const float* bias, uint8_t* dst) {
-            float v[32];
-            const int col0 = wg * 32;
-            tmem_ld32(tmem + lane_base + col0, v);
+            float v[16];
+            const int col0 = part * 16;
+            tmem_ld16(tmem + lane_base + col0, v);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < 2; j++) {
                 float o[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) o[i] = fmaxf(v[j * 8 + i] + __ldg(bias + col0 + j * 8 + i), 0.f);
@@ -290,11 +390,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
         };
         // dgrad epilogue: dZ_prev = acc * (act > 0) -> DZ tile (64 columns); bias gradient of the previous layer
         auto ep_mask = [&](const uint8_t* act, float* gbias, float inv_scale) {
-            float v[32];
-            const int col0 = wg * 32;
-            tmem_ld32(tmem + lane_base + col0, v);
+            float v[16];
+            const int col0 = part * 16;
+            tmem_ld16(tmem + lane_base + col0, v);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < 2; j++) {
                 const int kc = col0 / 8 + j;
                 const uint4 a = *reinterpret_cast<const uint4*>(act + kc * 2048 + (m >> 3) * 128 + (m & 7) * 16);
                 const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
@@ -308,8 +408,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
                 }
                 store_core(DZ, m, kc, o, X_LO);
             }
-            const float csum = warp_colsum32(v, lane);
-            atomicAdd(cs + col0 + lane, csum);
+            const float csum = warp_colsum16(v, lane);
+            atomicAdd(cs + col0 + (lane & 15), csum);
             bar_workers();
             if (tid < 64) {
                 const float s = cs[tid];
@@ -317,110 +417,63 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
                 cs[tid] = 0.f;
             }
         };
-        // grid backward from G[32][128] (feature gradients of the row-wise points pt3): table scatter + d/d(point) into gp[3][128]
-        auto grid_bwd = [&](const GridCtx& g, const float* pt3, float* gemb, float* gp, float inv_scale) {
-            for (int idx = tid; idx < 16 * TM; idx += NWORK) {
-                const int l = idx / TM, r = idx - l * TM;
-                if ((uint32_t)l >= g.n_levels) continue;
-                const float g0 = G[(2 * l) * TM + r] * inv_scale, g1 = G[(2 * l + 1) * TM + r] * inv_scale;
-                if (g0 == 0.f && g1 == 0.f) continue;
-                float u[3];
-#pragma unroll
-                for (int d = 0; d < 3; d++) u[d] = __fdiv_rn(__fadd_rn(pt3[d * TM + r], g.bound), g.two_bound);
-                if (u[0] < 0 || u[0] > 1 || u[1] < 0 || u[1] > 1 || u[2] < 0 || u[2] > 1) continue;
-                const LevelInfo L = g.lv[l];
-                const uint32_t res = L.res;
-                const float2* tab = reinterpret_cast<const float2*>(g.emb) + L.off;
-                float* gt = gemb + 2 * (size_t)L.off;
-                float pos[3], dv;
-                uint32_t pg[3], pg1[3];
-#pragma unroll
-                for (int d = 0; d < 3; d++) { pos[d] = locate(u[d], res, false, 0, pg[d], dv); pg1[d] = min(pg[d] + 1, res - 1); }
-                uint32_t cidx[8];
-#pragma unroll
-                for (uint32_t c = 0; c < 8; c++) {
-                    float w = 1.0f;
-#pragma unroll
-                    for (uint32_t d = 0; d < 3; d++) w = __fmul_rn(w, (c & (1u << d)) ? pos[d] : __fsub_rn(1.0f, pos[d]));
-                    cidx[c] = corner_index(L, (c & 1) ? pg1[0] : pg[0], (c & 2) ? pg1[1] : pg[1], (c & 4) ? pg1[2] : pg[2]);
-                    red_add2(gt + 2 * cidx[c], w * g0, w * g1);
-                }
-                const float scale = (float)res;
-#pragma unroll
-                for (uint32_t gd = 0; gd < 3; gd++) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (uint32_t i4 = 0; i4 < 4; i4++) {
-                        float w = scale;
-                        uint32_t cl = 0;
-#pragma unroll
-                        for (uint32_t nd = 0; nd < 2; nd++) {
-                            const uint32_t d = (nd >= gd) ? nd + 1 : nd;
-                            if (i4 & (1u << nd)) { w *= pos[d]; cl |= (1u << d); }
-                            else w *= (1.0f - pos[d]);
-                        }
-                        const float2 lo = __ldg(tab + cidx[cl]), hi = __ldg(tab + cidx[cl | (1u << gd)]);
-                        acc += w * ((hi.x - lo.x) * g0 + (hi.y - lo.y) * g1);
-                    }
-                    atomicAdd(gp + gd * TM + r, acc / g.two_bound);
-                }
-            }
-        };
-        // d(S0) epilogue (80 columns in the work accumulator): freq backward -> gp, grid columns -> G, topo columns -> returned
+        // d(S0) epilogue (80 columns in the work accumulator): every part moves 8 grid columns to G; parts 0..2 push two
+        // frequency bands each (columns 3+12*part .. 14+12*part) through sin/cos -> gp; part 0 adds the raw-point columns;
+        // part 3 returns the topo columns
         auto ep_ds0 = [&](const float* pt3, float* gp, float inv_scale, float& gt0, float& gt1) {
             gt0 = gt1 = 0.f;
-            if (wg == 0) {
-                float v[32], w[16];
-                tmem_ld32(tmem + lane_base, v);
-                tmem_ld16(tmem + lane_base + 32, w);           // columns 32..47: 32..38 freq, 39 pad, 40..47 grid levels 0..3
-                float f = 1.0f;
-                float acc[3] = {v[0], v[1], v[2]};
+            {
+                float w[8];
+                tmem_ld8(tmem + lane_base + 40 + 8 * part, w);
 #pragma unroll
-                for (int k = 0; k < 6; k++) {
-                    if (k < (int)p.n_freq) {
+                for (int i = 0; i < 8; i++) G[(8 * part + i) * TM + m] = w[i];
+            }
+            if (part < 3) {
+                float v[16];
+                tmem_ld16(tmem + lane_base + 12 * part, v);      // columns 12*part .. 12*part+15
+                float acc[3] = {0.f, 0.f, 0.f};
+                if (part == 0) { acc[0] = v[0]; acc[1] = v[1]; acc[2] = v[2]; }
+                float f = (part == 0) ? 1.0f : (part == 1 ? 4.0f : 16.0f);
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++) {
+                    if (2 * part + kk < (int)p.n_freq) {
 #pragma unroll
                         for (int a = 0; a < 3; a++) {
                             float sn, cn;
                             sincosf(pt3[a * TM + m] * f, &sn, &cn);
-                            const int is = 3 + 6 * k + a, ic = 6 + 6 * k + a;
-                            const float gs_ = is < 32 ? v[is] : w[is - 32];
-                            const float gc_ = ic < 32 ? v[ic] : w[ic - 32];
-                            acc[a] += f * (gs_ * cn - gc_ * sn);
+                            acc[a] += f * (v[3 + 6 * kk + a] * cn - v[6 + 6 * kk + a] * sn);
                         }
                     }
                     f *= 2.0f;
                 }
 #pragma unroll
                 for (int a = 0; a < 3; a++) atomicAdd(gp + a * TM + m, acc[a] * inv_scale);
-#pragma unroll
-                for (int i = 0; i < 8; i++) G[i * TM + m] = w[8 + i];
             } else {
-                float v[32];
-                tmem_ld32(tmem + lane_base + 48, v);           // columns 48..79: 48..71 grid features 8..31, 72..73 topo, 74..79 pad
-#pragma unroll
-                for (int i = 0; i < 24; i++) G[(8 + i) * TM + m] = v[i];
-                gt0 = v[24] * inv_scale;
-                gt1 = v[25] * inv_scale;
+                float t4[4];
+                tmem_ld4(tmem + lane_base + 72, t4);             // columns 72, 73: topo
+                gt0 = t4[0] * inv_scale;
+                gt1 = t4[1] * inv_scale;
             }
         };
-        // flush one wgrad accumulator: rows = input features (tc order), columns n < ncols
+        // flush one wgrad accumulator: rows = input features (tc order), 16 columns per part
         auto flush_acc = [&](int wcol, const mb_layer_desc& L, int kind, int krows, int ncols, float inv_scale) {
             const int krow = warp_q * 32 + lane;
             int korig = (krow < krows) ? tc_korig(kind, krow) : -1;
             if (korig >= (int)L.K) korig = -1;
-            const int col0 = wg * 32;
+            const int col0 = part * 16;
             if (col0 >= ncols) return;                 // warp-uniform
-            float v[32];
-            tmem_ld32(tmem + lane_base + wcol + col0, v);
+            float v[16];
+            tmem_ld16(tmem + lane_base + wcol + col0, v);
             if (korig < 0) return;
             float* dst = GA + L.wt_off + (size_t)korig * L.N_pad + col0;
-            if (ncols - col0 >= 32) {
+            if (ncols - col0 >= 16) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) red_add4(dst + 4 * j, v[4 * j] * inv_scale, v[4 * j + 1] * inv_scale, v[4 * j + 2] * inv_scale, v[4 * j + 3] * inv_scale);
+                for (int j = 0; j < 4; j++) red_add4(dst + 4 * j, v[4 * j] * inv_scale, v[4 * j + 1] * inv_scale, v[4 * j + 2] * inv_scale, v[4 * j + 3] * inv_scale);
             } else {
                 for (int j = 0; j < ncols - col0; j++) red_add(dst + j, v[j] * inv_scale);
             }
         };
+        const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const uint32_t m0 = tile * TM;
@@ -456,32 +509,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
                 signal_z(); wait_acc(); ep_hidden(AR + p.sdf[0].b_off, X0);
                 signal_z(); wait_acc(); ep_hidden(AR + p.sdf[1].b_off, X1);
                 signal_z(); wait_acc();
-                if (wg == 0) {
-                    float v[32], w[16];
-                    tmem_ld32(tmem + lane_base, v);
-                    tmem_ld16(tmem + lane_base + 32, w);
+                {
+                    // h = acc[:, 0:33] + b : col 0 = sdf, cols 1..32 = geometric feature -> colour-net cores 4..7 (one per part)
+                    float v[16];
+                    tmem_ld16(tmem + lane_base + 8 * part, v);
                     const float* b2 = AR + p.sdf[2].b_off;
-                    ssdf[m] = v[0] + __ldg(b2);
+                    if (part == 0) ssdf[m] = v[0] + __ldg(b2);
                     if (do_color) {
+                        float o[8];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            float o[8];
-#pragma unroll
-                            for (int i = 0; i < 8; i++) { const int col = 1 + j * 8 + i; o[i] = (col < 32 ? v[col] : w[col - 32]) + __ldg(b2 + col); }
-                            store_core(X0, m, 4 + j, o, X_LO);
-                        }
+                        for (int i = 0; i < 8; i++) o[i] = v[1 + i] + __ldg(b2 + 8 * part + 1 + i);
+                        store_core(X0, m, 4 + part, o, X_LO);
                     }
                 }
                 if (do_color) {
                     const float pnt[3] = {sxw[m], sxw[TM + m], sxw[2 * TM + m]};
-                    build_grid_core_tc(X0, m, wg * 2, gc, wg * 8, pnt, X_LO);
-                    build_grid_core_tc(X0, m, wg * 2 + 1, gc, wg * 8 + 4, pnt, X_LO);
+                    gather_levels_tc(X0, m, 0, gc, 4 * part, 4, pnt, X_LO);
                     signal_z(); wait_acc(); ep_hidden(AR + p.color[0].b_off, X1);
                     signal_z(); wait_acc(); ep_hidden(AR + p.color[1].b_off, X2);
                     signal_z(); wait_acc();
-                    if (wg == 0) {
-                        float v[16];
-                        tmem_ld16(tmem + lane_base, v);
+                    if (part == 0) {
+                        float v[4];
+                        tmem_ld4(tmem + lane_base, v);
 #pragma unroll
                         for (int a = 0; a < 3; a++) salb[a * TM + m] = 1.0f / (1.0f + expf(-(v[a] + __ldg(AR + p.color[2].b_off + a))));
                     }
@@ -558,100 +607,111 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
                     gsd[m] = v;
                 }
             }
-            // per-tile scale: max |start-of-chain gradient|
+            // per-tile scale: max |start-of-chain gradient|  (rows live in threads tid < 128 = warps 0..3)
             {
-                float mx = 0.f;
                 if (tid < TM) {
-                    mx = fabsf(gsd[tid]);
+                    float mx = fabsf(gsd[tid]);
 #pragma unroll
                     for (int a = 0; a < 3; a++) mx = fmaxf(mx, fabsf(galb[a * TM + tid]));
 #pragma unroll
                     for (int q = 0; q < 6; q++) mx = fmaxf(mx, fabsf(gsq[q * TM + tid]));
-                }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                    gbeta_local += __shfl_xor_sync(0xffffffffu, gbeta_local, o);
+                    for (int o = 16; o > 0; o >>= 1) {
+                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                        gbeta_local += __shfl_xor_sync(0xffffffffu, gbeta_local, o);
+                    }
+                    if (lane == 0) { misc[warp] = mx; misc[8 + warp] = gbeta_local; }
                 }
-                if (lane == 0) { misc[warp] = mx; misc[8 + warp] = gbeta_local; }
                 bar_workers();
                 if (tid == 0) {
                     float mm = 0.f, gb = 0.f;
-                    for (int w8 = 0; w8 < 8; w8++) { mm = fmaxf(mm, misc[w8]); gb += misc[8 + w8]; }
+                    for (int w4 = 0; w4 < 4; w4++) { mm = fmaxf(mm, misc[w4]); gb += misc[8 + w4]; }
                     int e = 0;
                     if (mm > 0.f && isfinite(mm)) { frexpf(mm, &e); e = 10 - e; }
                     e = max(-100, min(100, e));
                     if (gb != 0.f && gr.g_beta) atomicAdd(gr.g_beta, gb);
-                    misc[0] = ldexpf(1.0f, e);
-                    misc[1] = ldexpf(1.0f, -e);
+                    misc[4] = ldexpf(1.0f, e);
+                    misc[5] = ldexpf(1.0f, -e);
                 }
                 bar_workers();
             }
-            const float scale = misc[0], inv_scale = misc[1];
+            const float scale = misc[4], inv_scale = misc[5];
             bar_workers();
 
             // ---- main query backward ----
             if (do_main) {
                 if (color_grad) {
                     // dZ of the colour output layer: 16 columns
-                    if (wg == 0) {
+                    if (part == 0) {
                         const float v[8] = {galb[m] * scale, galb[TM + m] * scale, galb[2 * TM + m] * scale, 0.f, 0.f, 0.f, 0.f, 0.f};
                         store_core(DZ, m, 0, v, X_LO);
-                    } else {
-                        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        store_core(DZ, m, 1, z, X_LO);
-                    }
-                    if (tid < TM) {
                         for (int a = 0; a < 3; a++) {
-                            float s = galb[a * TM + tid];
+                            float s = galb[a * TM + m];
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                             if (lane == 0 && s != 0.f) red_add(GA + p.color[2].b_off + a, s);
                         }
+                    } else if (part == 1) {
+                        store_core(DZ, m, 1, z8, X_LO);
                     }
                     signal_z(); wait_acc(); ep_mask(X2, GA + p.color[1].b_off, inv_scale);      // -> dZ colour L1
                     signal_z(); wait_acc(); ep_mask(X1, GA + p.color[0].b_off, inv_scale);      // -> dZ colour L0
                     signal_z(); wait_acc();
-                    // d(C0): columns 0..31 colour-grid features -> G ; columns 32..63 -> d(feat) = dZ2 columns 1..32
-                    if (wg == 0) {
-                        float v[32];
-                        tmem_ld32(tmem + lane_base, v);
+                    // d(C0): columns 0..31 colour-grid features -> G ; columns 32..63 = d(feat) = dZ2 columns 1..32 of the SDF net
+                    if (part < 2) {
+                        float v[16];
+                        tmem_ld16(tmem + lane_base + 16 * part, v);
 #pragma unroll
-                        for (int i = 0; i < 32; i++) G[i * TM + m] = v[i];
+                        for (int i = 0; i < 16; i++) G[(16 * part + i) * TM + m] = v[i];
                     } else {
                         float v[32];
-                        tmem_ld32(tmem + lane_base + 32, v);
-                        const float g0 = gsd[m] * scale;
-#pragma unroll
-                        for (int c5 = 0; c5 < 5; c5++) {
+                        tmem_ld32(tmem + lane_base + 32, v);          // v[i] = dZ2 column 1 + i
+                        if (part == 2) {
+                            const float g0 = gsd[m] * scale;
+                            const float o0[8] = {g0, v[0], v[1], v[2], v[3], v[4], v[5], v[6]};
+                            store_core(DZ, m, 0, o0, X_LO);
                             float o[8];
 #pragma unroll
-                            for (int i = 0; i < 8; i++) {
-                                const int col = c5 * 8 + i;           // dZ2 column: 0 = sdf, 1..32 = feature
-                                o[i] = (col == 0) ? g0 : (col <= 32 ? v[col - 1] : 0.f);
-                            }
-                            store_core(DZ, m, c5, o, X_LO);
+                            for (int i = 0; i < 8; i++) o[i] = v[7 + i];
+                            store_core(DZ, m, 1, o, X_LO);
+#pragma unroll
+                            for (int i = 0; i < 8; i++) o[i] = v[15 + i];
+                            store_core(DZ, m, 2, o, X_LO);
+                            float h16[16];
+#pragma unroll
+                            for (int i = 0; i < 16; i++) h16[i] = v[i];
+                            const float csum = warp_colsum16(h16, lane);
+                            atomicAdd(cs + (lane & 15), csum);
+                        } else {
+                            float o[8];
+#pragma unroll
+                            for (int i = 0; i < 8; i++) o[i] = v[23 + i];
+                            store_core(DZ, m, 3, o, X_LO);
+                            const float o4[8] = {v[31], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                            store_core(DZ, m, 4, o4, X_LO);
+                            store_core(DZ, m, 5, z8, X_LO);
+                            float h16[16];
+#pragma unroll
+                            for (int i = 0; i < 16; i++) h16[i] = v[16 + i];
+                            const float csum = warp_colsum16(h16, lane);
+                            atomicAdd(cs + 16 + (lane & 15), csum);
                         }
-                        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        store_core(DZ, m, 5, z, X_LO);
-                        // bias gradient of sdf L2, columns 1..32 (scaled) ; column 0 below
-                        const float csum = warp_colsum32(v, lane);
-                        atomicAdd(cs + lane, csum);
                     }
                     tc_fence_before();
                     bar_workers();
                     if (tid < 32) { const float s = cs[tid]; if (s != 0.f) red_add(GA + p.sdf[2].b_off + 1 + tid, s * inv_scale); cs[tid] = 0.f; }
-                    grid_bwd(gc, sxw, gr.g_emb_col, gxw, inv_scale);
+                    grid_bwd_runs(gc, sxw, G, gr.g_emb_col, gxw, inv_scale, 0, tid);
                     bar_workers();
                 } else {
-                    if (wg == 0) {
+                    if (part == 0) {
                         const float v[8] = {gsd[m] * scale, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                         store_core(DZ, m, 0, v, X_LO);
-                        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        store_core(DZ, m, 1, z, X_LO); store_core(DZ, m, 2, z, X_LO);
+                        store_core(DZ, m, 4, z8, X_LO);
+                    } else if (part == 1) {
+                        store_core(DZ, m, 1, z8, X_LO);
+                        store_core(DZ, m, 5, z8, X_LO);
                     } else {
-                        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        store_core(DZ, m, 3, z, X_LO); store_core(DZ, m, 4, z, X_LO); store_core(DZ, m, 5, z, X_LO);
+                        store_core(DZ, m, part, z8, X_LO);
                     }
                 }
                 if (tid < TM) {      // bias gradient of sdf L2, column 0
@@ -669,10 +729,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
                 signal_z(); wait_acc();
                 float gt0, gt1;
                 ep_ds0(sxw, gxw, inv_scale, gt0, gt1);
-                if (wg == 1 && topo_live) { gtopo[m] += gt0; gtopo[TM + m] += gt1; }
+                if (part == 3 && topo_live) { gtopo[m] += gt0; gtopo[TM + m] += gt1; }
                 tc_fence_before();
                 bar_workers();
-                grid_bwd(gs, sxw, gr.g_emb_sdf, gxw, inv_scale);
+                grid_bwd_runs(gs, sxw, G, gr.g_emb_sdf, gxw, inv_scale, 0, tid);
                 bar_workers();
             }
 
@@ -680,6 +740,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
             if (need_fd) {
                 const float* pt = (flags & MB_F_FD_WARPED) ? sxw : sx;
                 float* gdst = (flags & MB_F_FD_WARPED) ? gxw : gx;
+#pragma unroll 1
                 for (int j = 0; j < 6; j++) {
                     if (tid < TM) {
                         const int Q = j * TM + tid, s = Q / 6, q = Q - s * 6;
@@ -700,34 +761,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
                     signal_z(); wait_acc(); ep_hidden(AR + p.sdf[0].b_off, X0);
                     signal_z(); wait_acc(); ep_hidden(AR + p.sdf[1].b_off, X1);
                     // dZ2: only column 0 (the FD query uses the sdf output only)
-                    {
+                    if (part == 0) {
                         const int Q = j * TM + m, s = Q / 6, q = Q - s * 6;
                         const float g0 = gsq[q * TM + s];
-                        if (wg == 0) {
-                            const float v[8] = {g0 * scale, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                            store_core(DZ, m, 0, v, X_LO);
-                            float sred = g0;
+                        const float v[8] = {g0 * scale, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        store_core(DZ, m, 0, v, X_LO);
+                        float sred = g0;
 #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) sred += __shfl_xor_sync(0xffffffffu, sred, o);
-                            if (lane == 0 && sred != 0.f) red_add(GA + p.sdf[2].b_off, sred);
-                        } else {
-                            const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                            store_core(DZ, m, 1, z, X_LO);
-                        }
+                        for (int o = 16; o > 0; o >>= 1) sred += __shfl_xor_sync(0xffffffffu, sred, o);
+                        if (lane == 0 && sred != 0.f) red_add(GA + p.sdf[2].b_off, sred);
+                    } else if (part == 1) {
+                        store_core(DZ, m, 1, z8, X_LO);
                     }
                     signal_z(); wait_acc(); ep_mask(X1, GA + p.sdf[1].b_off, inv_scale);
                     signal_z(); wait_acc(); ep_mask(X0, GA + p.sdf[0].b_off, inv_scale);
                     signal_z(); wait_acc();
                     float gt0, gt1;
                     ep_ds0(spt, gpt, inv_scale, gt0, gt1);
-                    if (wg == 1 && topo_live) {
+                    if (part == 3 && topo_live) {
                         const int s = (j * TM + m) / 6;
                         atomicAdd(gtopo + s, gt0);
                         atomicAdd(gtopo + TM + s, gt1);
                     }
                     tc_fence_before();
                     bar_workers();
-                    grid_bwd(gs, spt, gr.g_emb_sdf, gpt, inv_scale);
+                    grid_bwd_runs(gs, spt, G, gr.g_emb_sdf, gpt, inv_scale, j * TM, tid);
                     bar_workers();
                     if (tid < TM) {
                         const int Q = j * TM + tid, s = Q / 6, q = Q - s * 6;

@@ -232,14 +232,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
 
         // SDF-net input at point pt[3]: cores 0-4 freq, 5-8 grid, 9 topo
         auto build_sdf_input = [&](const float* pt3, const float* topo2) {
-            float pnt[3] = {pt3[m], pt3[TM + m], pt3[2 * TM + m]};
+            const float pnt[3] = {pt3[m], pt3[TM + m], pt3[2 * TM + m]};
             if (wg == 0) {
-                build_freq_tc(A, m, pnt, (int)p.n_freq);
-                build_grid_core_tc(A, m, 5, gs, 0, pnt);
+#pragma unroll 1
+                for (int a = 0; a < 3; a++) freq_axis_tc(A, m, a, pt3[a * TM + m], (int)p.n_freq);
+                store_one(A, m, 39, 0.f);
+                gather_levels_tc(A, m, 40, gs, 0, 4, pnt);
             } else {
-                build_grid_core_tc(A, m, 6, gs, 4, pnt);
-                build_grid_core_tc(A, m, 7, gs, 8, pnt);
-                build_grid_core_tc(A, m, 8, gs, 12, pnt);
+                gather_levels_tc(A, m, 40, gs, 4, 12, pnt);
                 float v[8] = {topo2[m], topo2[TM + m], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 store_core(A, m, 9, v);
             }
@@ -265,8 +265,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
                 for (int net = 0; net < 2; net++) {
                     const mb_layer_desc* L = net == 0 ? p.deform : p.topo;
                     if (wg == 0) {
-                        const float pnt[3] = {sx[m], sx[TM + m], sx[2 * TM + m]};
-                        build_freq_tc(A, m, pnt, (int)p.n_freq);
+#pragma unroll 1
+                        for (int a = 0; a < 3; a++) freq_axis_tc(A, m, a, sx[a * TM + m], (int)p.n_freq);
+                        store_one(A, m, 39, 0.f);
                     } else {
                         const float tt = st[m];
 #pragma unroll 1
@@ -339,8 +340,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
                 }
                 if (flags & MB_F_COLOR) {
                     const float pnt[3] = {sxw[m], sxw[TM + m], sxw[2 * TM + m]};
-                    build_grid_core_tc(A, m, wg * 2, gc, wg * 8, pnt);
-                    build_grid_core_tc(A, m, wg * 2 + 1, gc, wg * 8 + 4, pnt);
+                    gather_levels_tc(A, m, 0, gc, wg * 8, 8, pnt);
                     signal_a(c);
                     wait_acc(c);
                     epilogue_hidden<64>(c, AR + p.color[0].b_off, m, wg, warp_q);

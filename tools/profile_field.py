@@ -13,6 +13,14 @@ mode = sys.argv[1] if len(sys.argv) > 1 else 'fwd'
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 4096 * 128
 dev = torch.device('cuda:0')
 m = bench.make_state().to(dev).train()
+# "trained-like": the geometric init zeroes the sdf_net columns that read the hash grid (decoders.py:36-38), which would let the
+# backward skip the whole table scatter; a small perturbation makes every gradient path live, as after the first Adam step
+torch.manual_seed(1)
+with torch.no_grad():
+    for name, prm in m.named_parameters():
+        if 'embeddings' not in name:
+            prm.add_(0.02 * torch.randn_like(prm))
+m.invalidate()
 g = torch.Generator().manual_seed(0)
 x = ((torch.rand(M, 3, generator=g) * 2 - 1) * 0.6).to(dev)
 t = torch.full((M, 1), 0.3, device=dev)
