@@ -19,6 +19,9 @@
  *   mb_occ_update                    <- nerfacc OccGridEstimator.update_every_n_steps (morpheus.py:905-913)
  *   mb_adam_step                     <- torch.optim.Adam over get_params_all()   (morpheus.py:154-155)
  *   mb_sds_grad                      <- Zero123.train_step scalar math           (models/guidance/zero123_utils.py:177-212)
+ *   mb_ray_points_*                  <- xyzs = rays_o[ri] + rays_d[ri]*t         (morpheus.py:645-646)
+ *   mb_pack_arena_*                  <- nn.utils.weight_norm of MLP layers       (models/decoders.py:51-52)
+ *   mb_sdf_loss_*                    <- utils.get_sdf_loss                        (utils.py:91-113)
  */
 #ifndef MORPHEUS_B200_H
 #define MORPHEUS_B200_H
@@ -203,6 +206,27 @@ int mb_sds_grad(const float* eps_uncond, const float* eps_cond, const float* noi
 /* latents_noisy = sqrt(abar)*z + sqrt(1-abar)*eps */
 int mb_add_noise(const float* z, const float* eps, float sqrt_abar, float sqrt_one_minus_abar, float* out, uint32_t n,
                  mb_stream_t stream);
+
+/* ---- (8) host-glue kernels of the step (each replaces tens to hundreds of eager launches) ------------------------- */
+/* xyz[i] = rays_o[ray_indices[i]] + rays_d[ray_indices[i]] * (t_starts[i]+t_ends[i])/2        morpheus.py:645-646 */
+int mb_ray_points_forward(const float* rays_o, const float* rays_d, const int64_t* ray_indices, const float* t_starts,
+                          const float* t_ends, uint32_t M, float* xyz, mb_stream_t stream);
+/* g_o[r] = sum_i g_xyz[i], g_d[r] = sum_i g_xyz[i]*t_mid[i] over the packed samples seg[r]..seg[r+1] of ray r (either may be NULL) */
+int mb_ray_points_backward(const int32_t* seg, uint32_t N, const float* t_starts, const float* t_ends, const float* g_xyz,
+                           float* g_o, float* g_d, mb_stream_t stream);
+/* weight_norm + transpose + pad of the dense layers into the parameter arena (models/decoders.py:51-52 semantics).
+ * layer_table: n_layers x 8 int64 {weight_v|weight ptr, weight_g ptr or 0, bias ptr, K, N, K_pad, N_pad, wt_off} (device);
+ * backward writes d/d(weight_v|weight), d/d(weight_g), d/d(bias) into flat_grads at the float offsets of
+ * grad_table: n_layers x 4 int64 {gv_off, gg_off, gb_off, 0}. */
+int mb_pack_arena_forward(const int64_t* layer_table, int n_layers, float* arena, mb_stream_t stream);
+int mb_pack_arena_backward(const int64_t* layer_table, const int64_t* grad_table, int n_layers, const float* g_arena,
+                           float* flat_grads, mb_stream_t stream);
+/* utils.get_sdf_loss (utils.py:91-113) on packed samples: out2[0] += sum fs_i/n_i, out2[1] += sum |s_i-bound_i| band_i/n_i
+ * (caller zero-fills out2 and divides by count_nonzero(depth)); backward: g_sdf[i] = g_out2[0]*dfs_i + g_out2[1]*dsl_i. */
+int mb_sdf_loss_forward(const float* t_starts, const float* t_ends, const int64_t* ray_indices, const float* depth, const float* mask,
+                        const float* sdf, uint32_t M, float truncation, float* out2, mb_stream_t stream);
+int mb_sdf_loss_backward(const float* t_starts, const float* t_ends, const int64_t* ray_indices, const float* depth, const float* mask,
+                         const float* sdf, uint32_t M, float truncation, const float* g_out2, float* g_sdf, mb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -115,14 +115,24 @@ __device__ __forceinline__ uint32_t tile_lo(int t) { return t == 0 ? S0_LO : X_L
 // the same grid cell are merged in registers, so the table scatter costs one red.v2 per corner per CELL instead of
 // per row (the scatter is LSU-throughput bound).  d/d(point) by corner differencing as kernel_input_backward.
 __device__ __noinline__ void grid_bwd_runs(const GridCtx g, const float* __restrict__ pt3, const float* __restrict__ G, float* __restrict__ gemb,
-                                    float* __restrict__ gp, float inv_scale, int qbase, int tid) {
+                                            float* __restrict__ gp, float inv_scale, int qbase, int tid) {
+    // grid backward from G[32][128] (feature gradients of the row-wise points pt3, row r <-> query index qbase + r):
+    // work item = (run of <= 6 consecutive rows aligned to multiples of 6 in query space, level).  A run is the +-eps
+    // queries of ONE sample in an FD sub-tile (6 neighbouring samples of a ray in the main sub-tile).  Rows of a run that
+    // fall into the same grid cell are merged in registers, so the table scatter costs one red.v2 per corner per CELL
+    // instead of per row (the scatter is LSU-throughput bound).  The 16 levels of a run sit in the 16 lanes of a half-warp:
+    // d/d(point) (corner differencing, as kernel_input_backward) is summed over levels with shuffles and added to gp by
+    // one lane without atomics (a row belongs to exactly one run).
+    const int lane = tid & 31;
     const int run0 = qbase / 6;
     const int nruns = (qbase + TM - 1) / 6 - run0 + 1;
-    const int items = (int)min(g.n_levels, 16u) * nruns;
-    for (int it = tid; it < items; it += NWORK) {
-        const int l = it / nruns, rr = it - l * nruns;
-        const int q0 = max((run0 + rr) * 6, qbase), q1 = min((run0 + rr) * 6 + 6, qbase + TM);
-        const LevelInfo L = g.lv[l];
+    const int nl = (int)min(g.n_levels, 16u);
+    const int items = nruns * 16;
+    for (int it0 = (tid & ~31); it0 < items; it0 += NWORK) {       // warp-uniform trip count
+        const int it = it0 + lane;
+        const int l = it & 15, rr = it >> 4;
+        const bool live = rr < nruns && l < nl;
+        const LevelInfo L = g.lv[live ? l : 0];
         const uint32_t res = L.res;
         const float scale = (float)res;
         const float2* tab = reinterpret_cast<const float2*>(g.emb) + L.off;
@@ -133,58 +143,72 @@ __device__ __noinline__ void grid_bwd_runs(const GridCtx g, const float* __restr
         float2 cv[8];
         float acc[16];
 #pragma unroll 1
-        for (int q = q0; q < q1; q++) {
-            const int r = q - qbase;
-            const float g0 = G[(2 * l) * TM + r] * inv_scale, g1 = G[(2 * l + 1) * TM + r] * inv_scale;
-            if (g0 == 0.f && g1 == 0.f) continue;
-            float u[3];
+        for (int i = 0; i < 6; i++) {
+            const int r = (run0 + rr) * 6 + i - qbase;
+            const bool rowok = live && r >= 0 && r < TM;
+            float dx[3] = {0.f, 0.f, 0.f};
+            if (rowok) {
+                const float g0 = G[(2 * l) * TM + r] * inv_scale, g1 = G[(2 * l + 1) * TM + r] * inv_scale;
+                float u[3];
 #pragma unroll
-            for (int d = 0; d < 3; d++) u[d] = __fdiv_rn(__fadd_rn(pt3[d * TM + r], g.bound), g.two_bound);
-            if (u[0] < 0 || u[0] > 1 || u[1] < 0 || u[1] > 1 || u[2] < 0 || u[2] > 1) continue;
-            float pos[3], dv;
-            uint32_t pg[3];
+                for (int d = 0; d < 3; d++) u[d] = __fdiv_rn(__fadd_rn(pt3[d * TM + r], g.bound), g.two_bound);
+                const bool inb = !(u[0] < 0 || u[0] > 1 || u[1] < 0 || u[1] > 1 || u[2] < 0 || u[2] > 1);
+                if (inb && !(g0 == 0.f && g1 == 0.f)) {
+                    float pos[3], dv;
+                    uint32_t pg[3];
 #pragma unroll
-            for (int d = 0; d < 3; d++) pos[d] = locate(u[d], res, false, 0, pg[d], dv);
-            if (!have || pg[0] != c0 || pg[1] != c1 || pg[2] != c2) {
-                if (have) {
+                    for (int d = 0; d < 3; d++) pos[d] = locate(u[d], res, false, 0, pg[d], dv);
+                    if (!have || pg[0] != c0 || pg[1] != c1 || pg[2] != c2) {
+                        if (have) {
 #pragma unroll
-                    for (int c = 0; c < 8; c++) red_add2(gt + 2 * cidx[c], acc[2 * c], acc[2 * c + 1]);
-                }
-                have = true;
-                c0 = pg[0]; c1 = pg[1]; c2 = pg[2];
-                const uint32_t p1[3] = {min(pg[0] + 1, res - 1), min(pg[1] + 1, res - 1), min(pg[2] + 1, res - 1)};
+                            for (int c = 0; c < 8; c++) red_add2(gt + 2 * cidx[c], acc[2 * c], acc[2 * c + 1]);
+                        }
+                        have = true;
+                        c0 = pg[0]; c1 = pg[1]; c2 = pg[2];
+                        const uint32_t p1[3] = {min(pg[0] + 1, res - 1), min(pg[1] + 1, res - 1), min(pg[2] + 1, res - 1)};
 #pragma unroll
-                for (uint32_t c = 0; c < 8; c++) {
-                    cidx[c] = corner_index(L, (c & 1) ? p1[0] : pg[0], (c & 2) ? p1[1] : pg[1], (c & 4) ? p1[2] : pg[2]);
-                    cv[c] = __ldg(tab + cidx[c]);
-                    acc[2 * c] = acc[2 * c + 1] = 0.f;
-                }
-            }
-#pragma unroll
-            for (uint32_t c = 0; c < 8; c++) {
-                float w = 1.0f;
-#pragma unroll
-                for (uint32_t d = 0; d < 3; d++) w = __fmul_rn(w, (c & (1u << d)) ? pos[d] : __fsub_rn(1.0f, pos[d]));
-                acc[2 * c] = __fmaf_rn(w, g0, acc[2 * c]);
-                acc[2 * c + 1] = __fmaf_rn(w, g1, acc[2 * c + 1]);
-            }
-#pragma unroll
-            for (uint32_t gd = 0; gd < 3; gd++) {
-                float a = 0.f;
-#pragma unroll
-                for (uint32_t i4 = 0; i4 < 4; i4++) {
-                    float w = scale;
-                    uint32_t cl = 0;
-#pragma unroll
-                    for (uint32_t nd = 0; nd < 2; nd++) {
-                        const uint32_t d = (nd >= gd) ? nd + 1 : nd;
-                        if (i4 & (1u << nd)) { w *= pos[d]; cl |= (1u << d); }
-                        else w *= (1.0f - pos[d]);
+                        for (uint32_t c = 0; c < 8; c++) {
+                            cidx[c] = corner_index(L, (c & 1) ? p1[0] : pg[0], (c & 2) ? p1[1] : pg[1], (c & 4) ? p1[2] : pg[2]);
+                            cv[c] = __ldg(tab + cidx[c]);
+                            acc[2 * c] = acc[2 * c + 1] = 0.f;
+                        }
                     }
-                    const float2 lo = cv[cl], hi = cv[cl | (1u << gd)];
-                    a += w * ((hi.x - lo.x) * g0 + (hi.y - lo.y) * g1);
+#pragma unroll
+                    for (uint32_t c = 0; c < 8; c++) {
+                        float w = 1.0f;
+#pragma unroll
+                        for (uint32_t d = 0; d < 3; d++) w = __fmul_rn(w, (c & (1u << d)) ? pos[d] : __fsub_rn(1.0f, pos[d]));
+                        acc[2 * c] = __fmaf_rn(w, g0, acc[2 * c]);
+                        acc[2 * c + 1] = __fmaf_rn(w, g1, acc[2 * c + 1]);
+                    }
+#pragma unroll
+                    for (uint32_t gd = 0; gd < 3; gd++) {
+                        float a = 0.f;
+#pragma unroll
+                        for (uint32_t i4 = 0; i4 < 4; i4++) {
+                            float w = scale;
+                            uint32_t cl = 0;
+#pragma unroll
+                            for (uint32_t nd = 0; nd < 2; nd++) {
+                                const uint32_t d = (nd >= gd) ? nd + 1 : nd;
+                                if (i4 & (1u << nd)) { w *= pos[d]; cl |= (1u << d); }
+                                else w *= (1.0f - pos[d]);
+                            }
+                            const float2 lo = cv[cl], hi = cv[cl | (1u << gd)];
+                            a += w * ((hi.x - lo.x) * g0 + (hi.y - lo.y) * g1);
+                        }
+                        dx[gd] = a / g.two_bound;
+                    }
                 }
-                atomicAdd(gp + gd * TM + r, a / g.two_bound);
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) dx[d] += __shfl_xor_sync(0xffffffffu, dx[d], o);
+            }
+            if (l == 0 && rowok) {
+#pragma unroll
+                for (int d = 0; d < 3; d++) gp[d * TM + r] += dx[d];
             }
         }
         if (have) {
@@ -255,7 +279,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
         n_ops_s = n;
         for (int i = 0; i < NSTAGE; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         mbar_init(acc_ready, 1);
-        mbar_init(z_ready, NWORK);
+        mbar_init(z_ready, NWORK / 32);        // one elected arrival per worker warp
         mbar_fence_init();
     }
     if (warp == NWORK / 32) tmem_alloc<512>(tmem_holder);
@@ -359,7 +383,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
         uint8_t* X2 = X0 + 65536;
         uint8_t* DZ = smem + Smem::DZ;
         auto bar_workers = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory"); };
-        auto signal_z = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(z_ready); };
+        auto signal_z = [&]() { fence_proxy_async(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(z_ready); };
         auto wait_acc = [&]() { mbar_wait(acc_ready, acc_count & 1); acc_count++; tc_fence_after(); };
 
         // S0 operand (80 columns) at the row-wise points pt3 with row-wise topo: every part gathers 4 grid levels (one core),

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_warp_tc_kernel(const mb
     if (tid == 0) {
         for (int i = 0; i < NSTAGE; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         mbar_init(acc_ready, 1);
-        mbar_init(z_ready, NWORK);
+        mbar_init(z_ready, NWORK / 32);
         mbar_init(sa_full, 1);
         mbar_init(sa_full + 1, 1);
         mbar_fence_init();
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_warp_tc_kernel(const mb
         const uint32_t lane_base = (uint32_t)(warp_q * 32) << 16;
         uint32_t acc_count = 0;
         auto bar_workers = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory"); };
-        auto signal_z = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(z_ready); };
+        auto signal_z = [&]() { fence_proxy_async(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(z_ready); };
         uint8_t* SZ = smem + Smem::SZ;
 
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {

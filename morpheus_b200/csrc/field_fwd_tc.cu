@@ -66,7 +66,8 @@ __device__ __forceinline__ void wait_acc(Ctx& c) {
 __device__ __forceinline__ void signal_a(Ctx& c) {
     fence_proxy_async();
     tc_fence_before();
-    mbar_arrive(c.a_ready);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(c.a_ready);     // one elected arrival per worker warp
 }
 
 // epilogue of a hidden layer: acc[:, 0:N] + bias -> ReLU -> next A operand (cores 0..N/8-1), columns split over the 2 warpgroups
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
         n_ops_s = n;
         for (int i = 0; i < NSTAGE; i++) { mbar_init(c.full + i, 1); mbar_init(c.empty + i, 1); }
         mbar_init(c.acc_ready, 1);
-        mbar_init(c.a_ready, NWORK);
+        mbar_init(c.a_ready, NWORK / 32);
         mbar_fence_init();
     }
     if (warp == NWORK / 32) tmem_alloc<128>(tmem_holder);

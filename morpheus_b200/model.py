@@ -222,6 +222,36 @@ def get_encoder(encoding, input_dim=3, multires=6, num_levels=16, level_dim=2, b
 
 
 # ------------------------------------------------------------------------------------------------
+# parameter arena: weight_norm + transpose + pad of the 18 dense layers in ONE launch (and one backward launch)
+# ------------------------------------------------------------------------------------------------
+class _PackArena(torch.autograd.Function):
+    """tensors (weight_v, weight_g, bias | weight, bias per layer) -> flat arena of packing.LAYOUT (mb_pack_arena_forward);
+    backward maps the flat gradient arena back onto the parameters (mb_pack_arena_backward).  Replaces ~20 eager ops per
+    layer and direction (norm, div, mul, pad, transpose, cat and their autograd nodes)."""
+
+    @staticmethod
+    def forward(ctx, owner, table, gtable, n_grad, *tensors):
+        arena = torch.empty(packing.ARENA_FLOATS, device=tensors[0].device, dtype=torch.float32)
+        check(_lib.lib().mb_pack_arena_forward(ptr(table), table.shape[0], ptr(arena), stream()), 'pack_arena_forward')
+        ctx.owner, ctx.table, ctx.gtable, ctx.n_grad = owner, table, gtable, n_grad
+        ctx.save_for_backward(*tensors)
+        return arena
+
+    @staticmethod
+    def backward(ctx, g_arena):
+        tensors = ctx.saved_tensors
+        flat = torch.empty(ctx.n_grad, device=g_arena.device, dtype=torch.float32)
+        check(_lib.lib().mb_pack_arena_backward(ptr(ctx.table), ptr(ctx.gtable), ctx.table.shape[0], ptr(g_arena.contiguous()), ptr(flat),
+                                                stream()), 'pack_arena_backward')
+        ctx.owner._arena_cache = None      # this graph is consumed: the next query packs again
+        grads, off = [], 0
+        for t in tensors:
+            grads.append(flat[off:off + t.numel()].view(t.shape))
+            off += t.numel()
+        return (None, None, None, None) + tuple(grads)
+
+
+# ------------------------------------------------------------------------------------------------
 # the fused query as an autograd op
 # ------------------------------------------------------------------------------------------------
 class _FieldQuery(torch.autograd.Function):
@@ -231,7 +261,7 @@ class _FieldQuery(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, x, t, light, topo_in, arena, emb_sdf, emb_col, code0, code1, code2, beta):
-        flags, shading, ratio, n_levels, n_freq, offsets, bound, S, H = cfg
+        flags, shading, ratio, n_levels, n_freq, offsets, bound, S, H, tcws = cfg
         M = x.shape[0]
         dev = x.device
         x = x.contiguous().float()
@@ -267,9 +297,7 @@ class _FieldQuery(torch.autograd.Function):
             needs_grad = any(ctx.needs_input_grad)   # (grad mode itself is off inside Function.forward)
             if _lib.USE_TC_BWD and (flags & F_WARP) and needs_grad:
                 stash = torch.empty(((M + 127) // 128) * 10 * 65536, dtype=torch.uint8, device=dev)
-            tcw = torch.empty(tabs[2], dtype=torch.uint8, device=dev)
-            with _lib.timed('pack_tc'):
-                check(_lib.lib().mb_pack_tc(ptr(arena.detach()), ptr(tabs[0]), 18, ptr(tcw), stream()), 'pack_tc')
+            tcw = tcws['f']
             with _lib.timed('field_fwd_main' if flags & F_MAIN else 'field_fwd_aux'):
                 check(_lib.lib().mb_field_forward_tc(_lib.C.byref(P), _lib.C.byref(io), ptr(tcw), ptr(tabs[1]), ptr(stash), stream()), 'field_forward_tc')
         else:
@@ -284,7 +312,7 @@ class _FieldQuery(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_sdf, g_sigma, g_color, g_normal, g_raw, g_deform, g_topo):
-        flags, shading, ratio, n_levels, n_freq, offsets, bound, S, H = ctx.cfg
+        flags, shading, ratio, n_levels, n_freq, offsets, bound, S, H, tcws = ctx.cfg
         x, t, light, topo_in, arena, emb_sdf, emb_col, c0, c1, c2, beta_d, deform, topo, normal_raw = ctx.saved_tensors
         M = x.shape[0]
         codes = [c0, c1, c2]
@@ -328,10 +356,7 @@ class _FieldQuery(torch.autograd.Function):
         if use_sdf_tc:
             tabs_f = _tc_tables(x.device)
             tabs_s = _tc_tables_small(x.device)
-            tcw_f = torch.empty(tabs_f[2], dtype=torch.uint8, device=x.device)
-            tcw_s = torch.empty(tabs_s[2], dtype=torch.uint8, device=x.device)
-            check(_lib.lib().mb_pack_tc(ptr(arena.detach()), ptr(tabs_f[0]), 18, ptr(tcw_f), stream()), 'pack_tc')
-            check(_lib.lib().mb_pack_tc(ptr(arena.detach()), ptr(tabs_s[0]), 6, ptr(tcw_s), stream()), 'pack_tc(dgrad sdf)')
+            tcw_f, tcw_s = tcws['f'], tcws['s']
             with _lib.timed('field_bwd_sdf_tc_main' if flags & F_MAIN else 'field_bwd_sdf_tc_aux'):
                 check(_lib.lib().mb_field_backward_sdf_tc(_lib.C.byref(P), _lib.C.byref(io), _lib.C.byref(G), ptr(tcw_f), ptr(tabs_f[1]),
                                                           ptr(tcw_s), ptr(tabs_s[1]), stream()), 'field_backward_sdf_tc')
@@ -340,8 +365,7 @@ class _FieldQuery(torch.autograd.Function):
                 check(_lib.lib().mb_field_backward(_lib.C.byref(P), _lib.C.byref(io), _lib.C.byref(G), stream()), 'field_backward')
         if stash is not None:
             tabs = _tc_tables_dgrad(x.device)
-            tcw_t = torch.empty(tabs[2], dtype=torch.uint8, device=x.device)
-            check(_lib.lib().mb_pack_tc(ptr(arena.detach()), ptr(tabs[0]), 12, ptr(tcw_t), stream()), 'pack_tc(dgrad)')
+            tcw_t = tcws['t']
             gcode_ptrs = (_lib.C.c_void_p * 3)(*[g.data_ptr() for g in g_codes])
             with _lib.timed('field_bwd_warp_tc'):
                 check(_lib.lib().mb_field_backward_warp_tc(_lib.C.byref(P), ptr(x), ptr(t), M, ptr(g_def_out), ptr(g_topo_out), ptr(stash),
@@ -389,18 +413,69 @@ class scene_representation(nn.Module):
             self.bg_net = MLP(self.in_dim_bg + self.in_dim_bg_t, 3, hidden_dim_bg, num_layers_bg, bias=True)
         self.sdf2density = LaplaceDensity({'beta': 0.1})
         self._arena_cache = None
+        self._pack_tab = None
 
     # -- packed parameters ----------------------------------------------------------------------------
+    def _pack_inputs(self):
+        tensors = []
+        for mlp in (self.deform_net, self.topo_net, self.sdf_net, self.color_net):
+            for lin in mlp.net:
+                tensors += [lin.weight_v, lin.weight_g, lin.bias] if mlp.uses_weight_norm else [lin.weight, lin.bias]
+        return tensors
+
+    def _pack_tables(self, tensors):
+        """device tables of mb_pack_arena_* (include/morpheus_b200.h), rebuilt only when a parameter's storage moves"""
+        key = tuple(t.data_ptr() for t in tensors)
+        if self._pack_tab is None or self._pack_tab[0] != key:
+            rows, grows, it, off = [], [], iter(tensors), 0
+            for name, mlp in (('deform', self.deform_net), ('topo', self.topo_net), ('sdf', self.sdf_net), ('color', self.color_net)):
+                for (wt_off, w_off, b_off, K, N, Kp, Np) in packing.LAYOUT[name]:
+                    if mlp.uses_weight_norm:
+                        v, g, b = next(it), next(it), next(it)
+                        rows.append([v.data_ptr(), g.data_ptr(), b.data_ptr(), K, N, Kp, Np, wt_off])
+                        grows.append([off, off + v.numel(), off + v.numel() + g.numel(), 0])
+                        off += v.numel() + g.numel() + b.numel()
+                    else:
+                        w, b = next(it), next(it)
+                        rows.append([w.data_ptr(), 0, b.data_ptr(), K, N, Kp, Np, wt_off])
+                        grows.append([off, -1, off + w.numel(), 0])
+                        off += w.numel() + b.numel()
+                    for t in (rows[-1][0], rows[-1][2]):
+                        assert t % 4 == 0
+            dev = tensors[0].device
+            self._pack_tab = (key, torch.tensor(rows, dtype=torch.int64, device=dev), torch.tensor(grows, dtype=torch.int64, device=dev), off)
+        return self._pack_tab[1:]
+
     def packed_arena(self):
-        """Flat effective-weight arena (differentiable).  Rebuilt per call while training; cached under no_grad
-        until `invalidate()` (eval renders, occupancy refresh)."""
-        if not torch.is_grad_enabled() and self._arena_cache is not None:
-            return self._arena_cache
-        arena = packing.pack({'deform': self.deform_net.effective(), 'topo': self.topo_net.effective(),
-                              'sdf': self.sdf_net.effective(), 'color': self.color_net.effective()})
-        if not torch.is_grad_enabled():
-            self._arena_cache = arena
-        return arena
+        """(flat effective-weight arena, tensor-core operand tables).  Packed by ONE launch (differentiable through
+        _PackArena) and cached until a parameter changes (version counters), the arena's backward has run, or `invalidate()`
+        is called (optimisers that update parameters through raw pointers, e.g. train.FlatAdam, must call it)."""
+        tensors = self._pack_inputs()
+        for t in tensors:
+            if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+                raise RuntimeError('morpheus_b200: MLP parameters must be contiguous fp32 CUDA tensors (there is no CPU path)')
+        key = (torch.is_grad_enabled(), tuple((t.data_ptr(), t._version) for t in tensors))
+        c = self._arena_cache
+        if c is not None and c[0] == key:
+            return c[1], c[2]
+        table, gtable, n_grad = self._pack_tables(tensors)
+        arena = _PackArena.apply(self, table, gtable, n_grad, *tensors)
+        tcw = self._pack_tc(arena.detach()) if _lib.USE_TC else None
+        self._arena_cache = (key, arena, tcw)
+        return arena, tcw
+
+    @staticmethod
+    def _pack_tc(arena):
+        """fp16 (hi, lo) tensor-core operand slabs of the arena: forward table, dgrad table of the deform/topology nets,
+        dgrad table of the SDF/colour nets (mb_pack_tc); shared by every query and backward until the arena changes"""
+        dev = arena.device
+        out = {}
+        for name, (tabs, n) in (('f', (_tc_tables(dev), 18)), ('t', (_tc_tables_dgrad(dev), 12)), ('s', (_tc_tables_small(dev), 6))):
+            w = torch.empty(tabs[2], dtype=torch.uint8, device=dev)
+            with _lib.timed('pack_tc'):
+                check(_lib.lib().mb_pack_tc(ptr(arena), ptr(tabs[0]), n, ptr(w), stream()), 'pack_tc')
+            out[name] = w
+        return out
 
     def invalidate(self):
         self._arena_cache = None
@@ -422,8 +497,16 @@ class scene_representation(nn.Module):
         enc = self.encoder
         cfg = (int(flags), int(shading), float(ratio), n_levels, n_freq, enc.offsets, float(self.bound),
                float(np.log2(enc.per_level_scale)), int(enc.base_resolution))
+        tcw = None
         if arena is None:
-            arena = self.packed_arena()
+            arena, tcw = self.packed_arena()
+            if _lib.USE_TC and tcw is None:      # engine switched on after the arena was packed (tests toggle it)
+                tcw = self._pack_tc(arena.detach())
+                if self._arena_cache is not None and self._arena_cache[1] is arena:
+                    self._arena_cache = (self._arena_cache[0], arena, tcw)
+        elif _lib.USE_TC:
+            tcw = self._pack_tc(arena.detach())
+        cfg = cfg + (tcw,)
         v = self.deform_code.volumes
         return _FieldQuery.apply(cfg, x, t, light, topo_in, arena, self.encoder.embeddings, self.encoder_c.embeddings,
                                  v[0], v[1], v[2], self.sdf2density.get_beta())

@@ -9,8 +9,73 @@ reference.
 """
 import torch
 
+from . import _lib
 from . import nerfacc_compat as nerfacc
+from ._lib import check, ptr, stream
 from .model import safe_normalize
+
+
+class _RayPoints(torch.autograd.Function):
+    """xyzs = rays_o[ray_indices] + rays_d[ray_indices] * (t_starts + t_ends) / 2  (morpheus.py:645-646) in one launch; the
+    backward is a warp-per-ray segmented sum (mb_ray_points_backward) instead of two index_put(accumulate) kernels."""
+
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, ray_indices, t_starts, t_ends, seg):
+        rays_o, rays_d = rays_o.contiguous().float(), rays_d.contiguous().float()
+        M = ray_indices.shape[0]
+        xyz = torch.empty(M, 3, device=rays_o.device, dtype=torch.float32)
+        check(_lib.lib().mb_ray_points_forward(ptr(rays_o), ptr(rays_d), ptr(ray_indices), ptr(t_starts), ptr(t_ends), M, ptr(xyz), stream()),
+              'ray_points_forward')
+        ctx.save_for_backward(t_starts, t_ends, seg)
+        ctx.n_rays = rays_o.shape[0]
+        return xyz
+
+    @staticmethod
+    def backward(ctx, g_xyz):
+        t_starts, t_ends, seg = ctx.saved_tensors
+        N = ctx.n_rays
+        g_o = torch.empty(N, 3, device=g_xyz.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        g_d = torch.empty(N, 3, device=g_xyz.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        if g_o is not None or g_d is not None:
+            check(_lib.lib().mb_ray_points_backward(ptr(seg), N, ptr(t_starts), ptr(t_ends), ptr(g_xyz.contiguous().float()), ptr(g_o), ptr(g_d),
+                                                    stream()), 'ray_points_backward')
+        return g_o, g_d, None, None, None, None
+
+
+class _SdfLoss(torch.autograd.Function):
+    """utils.get_sdf_loss (utils.py:91-113) over the packed samples in one launch: -> [2] = (sum fs_i/n_i, sum sdf_i/n_i)."""
+
+    @staticmethod
+    def forward(ctx, sdf, t_starts, t_ends, ray_indices, depth, mask, trunc):
+        sdf = sdf.contiguous().float()
+        out = torch.zeros(2, device=sdf.device, dtype=torch.float32)
+        check(_lib.lib().mb_sdf_loss_forward(ptr(t_starts), ptr(t_ends), ptr(ray_indices), ptr(depth), ptr(mask), ptr(sdf), sdf.shape[0],
+                                             _lib.C.c_float(trunc), ptr(out), stream()), 'sdf_loss_forward')
+        ctx.save_for_backward(sdf, t_starts, t_ends, ray_indices, depth, mask)
+        ctx.trunc = trunc
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        sdf, t_starts, t_ends, ray_indices, depth, mask = ctx.saved_tensors
+        g_sdf = torch.empty_like(sdf)
+        check(_lib.lib().mb_sdf_loss_backward(ptr(t_starts), ptr(t_ends), ptr(ray_indices), ptr(depth), ptr(mask), ptr(sdf), sdf.shape[0],
+                                              _lib.C.c_float(ctx.trunc), ptr(g_out.contiguous().float()), ptr(g_sdf), stream()), 'sdf_loss_backward')
+        return g_sdf, None, None, None, None, None, None
+
+
+def packed_sdf_loss(sdf, t_starts, t_ends, ray_indices, rays_depth, rays_mask, truncation, rays_w_depth=None):
+    """get_sdf_loss(z_vals=(t0+t1)/2, target_d=depth[ray], sdf, truncation, mask=mask[ray]) without materialising any
+    per-sample intermediate.  rays_w_depth: see get_sdf_loss."""
+    depth = rays_depth.reshape(-1).contiguous().float()
+    mask = rays_mask.reshape(-1).contiguous().float() if rays_mask is not None else None
+    out = _SdfLoss.apply(sdf, t_starts, t_ends, ray_indices, depth, mask, float(truncation))
+    if rays_w_depth is None:
+        # count_nonzero(target_d) over SAMPLES (utils.py:107): every sample of a ray with depth != 0 counts
+        seg_len = torch.bincount(ray_indices, minlength=depth.shape[0])
+        rays_w_depth = (seg_len * (depth != 0)).sum()
+    out = out / rays_w_depth
+    return out[0], out[1]
 
 
 def get_camera_rays(H, W, fx, fy=None, cx=None, cy=None, device='cuda'):
@@ -121,8 +186,11 @@ class Renderer:
         ray_indices = ray_indices.long()
         if light_d is None:
             light_d = safe_normalize(rays_o + torch.randn(3, device=rays_o.device))
-        t_positions = ((t_starts + t_ends) / 2.0)[..., None]
-        xyzs = rays_o[ray_indices] + rays_d[ray_indices] * t_positions
+        t_starts, t_ends = t_starts.contiguous().float(), t_ends.contiguous().float()
+        ray_indices = ray_indices.contiguous()
+        seg = nerfacc.ray_segments(ray_indices, N) if ray_indices.shape[0] > 0 else None
+        xyzs = (_RayPoints.apply(rays_o, rays_d, ray_indices, t_starts, t_ends, seg) if ray_indices.shape[0] > 0
+                else torch.zeros(0, 3, device=rays_o.device))
         time_step = rays_t[ray_indices]
         sdf = None
         if xyzs.shape[0] == 0:  # morpheus.py:663-670 (sdf defined here; the reference would raise NameError at :701)
@@ -132,7 +200,7 @@ class Renderer:
         else:
             light = light_d[ray_indices] if shading != 'albedo' else None
             sdf, sigmas, rgbs, normals, deform, normal_raw = model(xyzs, time_step, light, ratio=ambient_ratio, shading=shading, cano=cano)
-            weights, opacity, depth, rgb = nerfacc.composite(sigmas, rgbs, t_starts, t_ends, ray_indices, N)
+            weights, opacity, depth, rgb = nerfacc.composite(sigmas, rgbs, t_starts, t_ends, ray_indices, N, seg=seg)
             opacity = opacity[:, None]
             if bg_color is None:
                 if cfg['model']['bg_radius'] > 0 and cano and (not real_view):
@@ -158,17 +226,18 @@ class Renderer:
                 results['loss_normal_perturb'] = (normals - normals_perturb).abs().mean()
             if tr['code_reg'] > 0 and not cano:
                 ts = time_step[:1]
-                code = model.get_deform_code(ts)
-                code_prev = model.get_deform_code(ts - 1 / self.num_frames)
-                code_next = model.get_deform_code(ts + 1 / self.num_frames)
-                results['loss_code'] = torch.square(2 * code - code_prev - code_next).mean()
+                # morpheus.py:766-771: code(t), code(t - 1/F), code(t + 1/F) -- sampled in ONE batched call (same arithmetic per row)
+                codes = model.get_deform_code(torch.cat([ts, ts - 1 / self.num_frames, ts + 1 / self.num_frames], dim=0))
+                results['loss_code'] = torch.square(2 * codes[0:1] - codes[1:2] - codes[2:3]).mean()
             if rays_depth is not None:
-                t_gt = rays_depth[ray_indices]
-                t_mask = rays_mask[ray_indices] if rays_mask is not None else None
                 if self.sdf_count_override is not None:
                     cnt = self.sdf_count_override
+                elif self.uniform_samples:
+                    cnt = torch.count_nonzero(rays_depth) * self.uniform_samples      # == count_nonzero(depth[ray_indices])
+                    if self.world_size > 1:
+                        cnt = global_count(cnt, self.world_size)
                 else:
-                    cnt = global_count(torch.count_nonzero(t_gt), self.world_size) if self.world_size > 1 else None
-                fs_loss, sdf_loss = get_sdf_loss(t_positions, t_gt, sdf, tr['trunc'], mask=t_mask, rays_w_depth=cnt)
+                    cnt = global_count(torch.count_nonzero(rays_depth[ray_indices]), self.world_size) if self.world_size > 1 else None
+                fs_loss, sdf_loss = packed_sdf_loss(sdf, t_starts, t_ends, ray_indices, rays_depth, rays_mask, tr['trunc'], rays_w_depth=cnt)
                 results['sdf_loss'], results['fs_loss'] = sdf_loss, fs_loss
         return results

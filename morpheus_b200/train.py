@@ -76,6 +76,7 @@ class FlatAdam:
         self.betas, self.eps, self.t, self.n = betas, eps, 0, n
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # device-side step count (CUDA-graph replayable)
         self.params = plist
+        self.model = model
 
     def set_group_lr(self, name, lr):
         self.group_lr[self.group_names.index(name)] = lr
@@ -94,6 +95,7 @@ class FlatAdam:
             check(_lib.lib().mb_adam_step_dev(ptr(self.flat), ptr(self.grad), ptr(self.m), ptr(self.v), ptr(self.group_id), ptr(self.group_lr),
                                               C.c_uint64(self.n), C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
                                               ptr(self.step_dev), stream()), 'adam_step')
+        self.model.invalidate()    # parameters changed through raw pointers: version counters cannot see it
 
 
 def train_step(renderer, opt, batch, tr, world_size=1, shading='albedo_normal', samples=None):

@@ -533,3 +533,77 @@ def test_tc_backward_sdf_matches_simt(dev, case):
         errs.pop('sdf_net.net.2.bias', None)   # the last-layer bias cancels exactly in the +-eps differences: its gradient is pure round-off
     bad = {n: e for n, e in errs.items() if e > 3e-4}
     assert not bad, f'{bad}\nall: {errs}'
+
+
+# ------------------------------------------------------------------------------------------------
+# host-glue kernels (csrc/glue.cu)
+# ------------------------------------------------------------------------------------------------
+def test_pack_arena_matches_torch_weight_norm(dev):
+    """mb_pack_arena_* == the differentiable torch construction (packing.pack over MLP.effective(): v * g / ||v||,
+    models/decoders.py:51-52), forward bit-close and parameter gradients to 1e-6."""
+    from morpheus_b200 import packing
+    from oracle.fields import init_reference_like_state
+    sd = init_reference_like_state(200, seed=5, randomize=True, emb_scale=0.05)
+    m = make_model(sd, 1.0, dev).train()
+    ref = packing.pack({'deform': m.deform_net.effective(), 'topo': m.topo_net.effective(), 'sdf': m.sdf_net.effective(),
+                        'color': m.color_net.effective()})
+    arena, tcw = m.packed_arena()
+    assert arena.shape == ref.shape
+    assert rel_l2(cpu(arena), cpu(ref)) < 1e-7
+    assert float((arena - ref).abs().max()) < 1e-6
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(ref.shape, generator=g).to(dev)
+    # only the Wt and b slots of the gradient arena are populated by the kernels: mask the W (n-major) slots
+    mask = torch.zeros_like(w)
+    for net in packing.NET_ORDER:
+        for (wt_off, w_off, b_off, K, N, Kp, Np) in packing.LAYOUT[net]:
+            mask[wt_off:wt_off + Kp * Np] = 1
+            mask[b_off:b_off + Np] = 1
+    w = w * mask
+    params = [p for n_, p in m.named_parameters() if any(k in n_ for k in ('deform_net', 'topo_net', 'sdf_net', 'color_net'))]
+    g_ref = torch.autograd.grad((ref * w).sum(), params)
+    g_new = torch.autograd.grad((arena * w).sum(), params)
+    for a, b, (n_, _) in zip(g_new, g_ref, [(n_, p) for n_, p in m.named_parameters() if any(k in n_ for k in ('deform_net', 'topo_net', 'sdf_net', 'color_net'))]):
+        assert rel_l2(cpu(a), cpu(b)) < 2e-6, n_
+    # the cache is dropped once the arena's backward has run, and after invalidate()
+    arena2, _ = m.packed_arena()
+    assert arena2 is not arena
+
+
+def test_ray_points_and_sdf_loss_match_torch(dev):
+    from morpheus_b200 import render as mr
+    from morpheus_b200.nerfacc_compat import ray_segments
+    g = torch.Generator().manual_seed(3)
+    N = 257
+    counts = torch.randint(0, 40, (N,), generator=g)
+    counts[5] = 0
+    ri = torch.repeat_interleave(torch.arange(N), counts).to(dev)
+    M = ri.shape[0]
+    o = torch.randn(N, 3, generator=g).to(dev).requires_grad_(True)
+    d = torch.randn(N, 3, generator=g).to(dev).requires_grad_(True)
+    t0 = (torch.rand(M, generator=g) * 3).to(dev)
+    t1 = t0 + 0.01
+    seg = ray_segments(ri, N)
+    xyz = mr._RayPoints.apply(o, d, ri, t0, t1, seg)
+    ref = o[ri] + d[ri] * ((t0 + t1) / 2.0)[:, None]
+    assert torch.equal(xyz, ref)          # bit-exact: same two roundings (mul, add)
+    w = torch.randn(M, 3, generator=g).to(dev)
+    ga = torch.autograd.grad((xyz * w).sum(), [o, d])
+    gb = torch.autograd.grad((ref * w).sum(), [o, d])
+    for a, b in zip(ga, gb):
+        assert float((a - b).abs().max()) < 1e-4 * float(b.abs().max())
+    # get_sdf_loss (utils.py:91-113): depth with holes (0), invalid (-1), masks, samples in front / inside / behind the band
+    depth = (torch.rand(N, 1, generator=g) * 3 + 0.2)
+    depth[::7] = 0.0
+    depth[3::11] = -1.0
+    mask = (torch.rand(N, 1, generator=g) > 0.3).float()
+    depth, mask = depth.to(dev), mask.to(dev)
+    sdf = (torch.randn(M, generator=g) * 0.2).to(dev).requires_grad_(True)
+    z = ((t0 + t1) / 2.0)[:, None]
+    fs_ref, sl_ref = mr.get_sdf_loss(z, depth[ri], sdf, 0.1, mask=mask[ri])
+    fs, sl = mr.packed_sdf_loss(sdf, t0, t1, ri, depth, mask, 0.1)
+    assert abs(float(fs) - float(fs_ref)) < 1e-5 * max(1.0, abs(float(fs_ref)))
+    assert abs(float(sl) - float(sl_ref)) < 1e-5 * max(1.0, abs(float(sl_ref)))
+    ga = torch.autograd.grad(2.0 * fs + 3.0 * sl, sdf)[0]
+    gb = torch.autograd.grad(2.0 * fs_ref + 3.0 * sl_ref, sdf)[0]
+    assert rel_l2(cpu(ga), cpu(gb)) < 1e-5
