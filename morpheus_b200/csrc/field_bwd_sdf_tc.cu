@@ -64,8 +64,9 @@ struct Smem {
     static constexpr int GSQ = GTOPO + 2 * 512;          // [6]
     static constexpr int GALB = GSQ + 6 * 512;           // [3]
     static constexpr int GSD = GALB + 3 * 512;           // [1]  d/d(sdf) of the main query
-    static constexpr int CS = GSD + 512;                 // [1]  column sums
-    static constexpr int MISC = CS + 512;                // 16 floats
+    static constexpr int CS = GSD + 512;                 // [1]  column sums (sdf L2 feature columns, colour path)
+    static constexpr int CSB = CS + 512;                 // [2]  per-tile bias-gradient accumulators: sdf1 | sdf0 | col1 | col0 (64 each)
+    static constexpr int MISC = CSB + 2 * 512;           // 16 floats
     static constexpr int OPS = MISC + 64;                // OpS[MAX_OPS]
     static constexpr int BAR = OPS + MAX_OPS * 16;       // full[3], empty[3], acc_ready, z_ready
     static constexpr int TMEMH = BAR + 8 * (2 * NSTAGE + 2);
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
     float* galb = reinterpret_cast<float*>(smem + Smem::GALB);
     float* gsd = reinterpret_cast<float*>(smem + Smem::GSD);
     float* cs = reinterpret_cast<float*>(smem + Smem::CS);
+    float* csb = reinterpret_cast<float*>(smem + Smem::CSB);
     float* misc = reinterpret_cast<float*>(smem + Smem::MISC);
     float* G = reinterpret_cast<float*>(smem + Smem::G);
     OpS* ops = reinterpret_cast<OpS*>(smem + Smem::OPS);
@@ -274,7 +276,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
         if (need_fd)
             for (int j = 0; j < 6; j++) {
                 fwd(0, 5, 64, 0); fwd(1, 4, 64, 1);
-                bwd(2, 1, 64, 2, 16, 256); bwd(1, 4, 64, 1, 64, 192); bwd(0, 4, 80, 0, 64, 128);
+                bwd(1, 4, 64, 1, 64, 192); ops[n - 1].kind = 2;      // + layer-2 weight gradient from the 16-column dZ2 side tile
+                bwd(0, 4, 80, 0, 64, 128);
             }
         n_ops_s = n;
         for (int i = 0; i < NSTAGE; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
@@ -325,7 +328,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
                 mbar_wait(z_ready, z_count & 1);
                 z_count++;
                 tc_fence_after();
-                if (o.kind == 1) {
+                if (o.kind == 2) {
+                    // ---- FD chain: layer-2 weight gradient acc[256][k][0:16] (+)= A2^T dZ2 (dZ2 = 16-column side tile in G) ----
+                    const uint32_t a_base = sm_base + tile_base(2), g_base = sm_base + Smem::G;
+                    const uint32_t idesc = make_idesc_f16(16) | (1u << 15) | (1u << 16);
+                    const bool first = !(used_mask & 4u);
+                    used_mask |= 4u;
+                    const uint64_t a_hi0 = make_smem_desc(a_base, 128, 2048), a_lo0 = make_smem_desc(a_base + X_LO, 128, 2048);
+                    const uint64_t b_hi0 = make_smem_desc(g_base, 128, 2048), b_lo0 = make_smem_desc(g_base + 4096, 128, 2048);
+#pragma unroll
+                    for (uint32_t s = 0; s < 8; s++) {
+                        umma_f16(tmem + 256, a_hi0 + s * 16, b_hi0 + s * 16, idesc, (first && s == 0) ? 0u : 1u);
+                        umma_f16(tmem + 256, a_hi0 + s * 16, b_lo0 + s * 16, idesc, 1u);
+                        umma_f16(tmem + 256, a_lo0 + s * 16, b_hi0 + s * 16, idesc, 1u);
+                    }
+                }
+                if (o.kind >= 1) {
                     // ---- wgrad: acc[wcol][k][n] (+)= A^T dZ ; both operands MN-major, K = 128 rows in 8 steps ----
                     const uint32_t a_base = sm_base + tile_base(o.a_tile), a_lo = tile_lo(o.a_tile);
                     const uint32_t idesc = make_idesc_f16(o.wn) | (1u << 15) | (1u << 16);
@@ -413,7 +431,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
             }
         };
         // dgrad epilogue: dZ_prev = acc * (act > 0) -> DZ tile (64 columns); bias gradient of the previous layer
-        auto ep_mask = [&](const uint8_t* act, float* gbias, float inv_scale) {
+        auto ep_mask = [&](const uint8_t* act, float* cacc) {
             float v[16];
             const int col0 = part * 16;
             tmem_ld16(tmem + lane_base + col0, v);
@@ -433,13 +451,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
                 store_core(DZ, m, kc, o, X_LO);
             }
             const float csum = warp_colsum16(v, lane);
-            atomicAdd(cs + col0 + (lane & 15), csum);
-            bar_workers();
-            if (tid < 64) {
-                const float s = cs[tid];
-                if (s != 0.f) red_add(gbias + tid, s * inv_scale);
-                cs[tid] = 0.f;
+            atomicAdd(cacc + col0 + (lane & 15), csum);      // bias gradient: flushed once per tile
+        };
+        // FD query, layer-1 forward epilogue fused with the layer-2 backward: A2 = relu(acc + b1) -> X1 (wgrad operand) and,
+        // because the query's only output is sdf = row 0 of layer 2, dZ1[m][k] = g0[m] * W2[0][k] * (A2 > 0) directly (rank-1:
+        // no dgrad MMA, no extra round trip); dZ2 = {g0, 0...} goes to a 16-column side tile for the layer-2 weight gradient
+        auto ep_hidden_fd = [&](float g0s) {
+            float v[16];
+            const int col0 = part * 16;
+            tmem_ld16(tmem + lane_base + col0, v);
+            const float* b1 = AR + p.sdf[1].b_off + col0;
+            const float* w2 = AR + p.sdf[2].w_off + col0;          // W[n = 0][k]
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                float o[8], z[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    o[i] = fmaxf(v[j * 8 + i] + __ldg(b1 + j * 8 + i), 0.f);
+                    z[i] = (o[i] > 0.f) ? g0s * __ldg(w2 + j * 8 + i) : 0.f;
+                    v[j * 8 + i] = z[i];
+                }
+                store_core(X1, m, col0 / 8 + j, o, X_LO);
+                store_core(DZ, m, col0 / 8 + j, z, X_LO);
             }
+            const float csum = warp_colsum16(v, lane);
+            atomicAdd(csb + col0 + (lane & 15), csum);
         };
         // d(S0) epilogue (80 columns in the work accumulator): every part moves 8 grid columns to G; parts 0..2 push two
         // frequency bands each (columns 3+12*part .. 14+12*part) through sin/cos -> gp; part 0 adds the raw-point columns;
@@ -525,6 +561,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
             }
             for (int idx = tid; idx < 6 * TM; idx += NWORK) gsq[idx] = 0.f;
             if (tid < TM) { gsd[tid] = 0.f; cs[tid] = 0.f; }
+            if (tid < 256) csb[tid] = 0.f;
             bar_workers();
 
             // ---- forward of the main query (needed for albedo / sdf / the colour-net input) ----
@@ -678,8 +715,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
                     } else if (part == 1) {
                         store_core(DZ, m, 1, z8, X_LO);
                     }
-                    signal_z(); wait_acc(); ep_mask(X2, GA + p.color[1].b_off, inv_scale);      // -> dZ colour L1
-                    signal_z(); wait_acc(); ep_mask(X1, GA + p.color[0].b_off, inv_scale);      // -> dZ colour L0
+                    signal_z(); wait_acc(); ep_mask(X2, csb + 128);      // -> dZ colour L1
+                    signal_z(); wait_acc(); ep_mask(X1, csb + 192);      // -> dZ colour L0
                     signal_z(); wait_acc();
                     // d(C0): columns 0..31 colour-grid features -> G ; columns 32..63 = d(feat) = dZ2 columns 1..32 of the SDF net
                     if (part < 2) {
@@ -748,8 +785,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
                     signal_z(); wait_acc(); ep_hidden(AR + p.sdf[0].b_off, X0);
                     signal_z(); wait_acc(); ep_hidden(AR + p.sdf[1].b_off, X1);
                 }
-                signal_z(); wait_acc(); ep_mask(X1, GA + p.sdf[1].b_off, inv_scale);
-                signal_z(); wait_acc(); ep_mask(X0, GA + p.sdf[0].b_off, inv_scale);
+                signal_z(); wait_acc(); ep_mask(X1, csb);
+                signal_z(); wait_acc(); ep_mask(X0, csb + 64);
                 signal_z(); wait_acc();
                 float gt0, gt1;
                 ep_ds0(sxw, gxw, inv_scale, gt0, gt1);
@@ -761,44 +798,62 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
             }
 
             // ---- finite-difference normal queries: 6 sub-tiles of (sample, query) rows, query index fastest ----
+            // per sub-tile: S0 -> [MMA] -> A1 -> [MMA] -> A2 & dZ1 (fused epilogue) -> [MMA: wgrad2, wgrad1, dgrad1] -> dZ0
+            //               -> [MMA: wgrad0, dgrad0] -> d(S0) -> frequency / grid backward           (4 round trips)
             if (need_fd) {
                 const float* pt = (flags & MB_F_FD_WARPED) ? sxw : sx;
                 float* gdst = (flags & MB_F_FD_WARPED) ? gxw : gx;
+                uint8_t* DZ2 = smem + Smem::G;            // 16-column dZ2 tile (hi 4 KB | lo 4 KB) in the idle G scratch
 #pragma unroll 1
-                for (int j = 0; j < 6; j++) {
+                for (int j = 0; j <= 6; j++) {
                     if (tid < TM) {
-                        const int Q = j * TM + tid, s = Q / 6, q = Q - s * 6;
-                        const int axis = q >> 1;
-                        const float e = (q & 1) ? -FD_EPS : FD_EPS;
+                        if (j > 0) {      // fold the point gradients of sub-tile j-1 into the sample gradients (clamp derivative)
+                            const int Q = (j - 1) * TM + tid, s = Q / 6, q = Q - s * 6;
+                            const int axis = q >> 1;
+                            const float e = (q & 1) ? -FD_EPS : FD_EPS;
 #pragma unroll
-                        for (int a = 0; a < 3; a++) {
-                            float v = pt[a * TM + s];
-                            if (a == axis) v = __fadd_rn(v, e);
-                            spt[a * TM + tid] = fminf(fmaxf(v, -p.bound), p.bound);
-                            gpt[a * TM + tid] = 0.f;
+                            for (int a = 0; a < 3; a++) {
+                                float v = pt[a * TM + s];
+                                if (a == axis) v = __fadd_rn(v, e);
+                                if (v >= -p.bound && v <= p.bound) atomicAdd(gdst + a * TM + s, gpt[a * TM + tid]);
+                            }
                         }
-                        stq[tid] = stopo[s];
-                        stq[TM + tid] = stopo[TM + s];
+                        if (j < 6) {
+                            const int Q = j * TM + tid, s = Q / 6, q = Q - s * 6;
+                            const int axis = q >> 1;
+                            const float e = (q & 1) ? -FD_EPS : FD_EPS;
+#pragma unroll
+                            for (int a = 0; a < 3; a++) {
+                                float v = pt[a * TM + s];
+                                if (a == axis) v = __fadd_rn(v, e);
+                                spt[a * TM + tid] = fminf(fmaxf(v, -p.bound), p.bound);
+                                gpt[a * TM + tid] = 0.f;
+                            }
+                            stq[tid] = stopo[s];
+                            stq[TM + tid] = stopo[TM + s];
+                        }
                     }
                     bar_workers();
+                    if (j == 6) break;
                     build_s0(spt, stq);
                     signal_z(); wait_acc(); ep_hidden(AR + p.sdf[0].b_off, X0);
-                    signal_z(); wait_acc(); ep_hidden(AR + p.sdf[1].b_off, X1);
-                    // dZ2: only column 0 (the FD query uses the sdf output only)
-                    if (part == 0) {
+                    signal_z(); wait_acc();
+                    {
                         const int Q = j * TM + m, s = Q / 6, q = Q - s * 6;
                         const float g0 = gsq[q * TM + s];
-                        const float v[8] = {g0 * scale, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        store_core(DZ, m, 0, v, X_LO);
-                        float sred = g0;
+                        ep_hidden_fd(g0 * scale);
+                        if (part == 0) {
+                            const float v[8] = {g0 * scale, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                            store_core(DZ2, m, 0, v, 4096);
+                            float sred = g0;
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) sred += __shfl_xor_sync(0xffffffffu, sred, o);
-                        if (lane == 0 && sred != 0.f) red_add(GA + p.sdf[2].b_off, sred);
-                    } else if (part == 1) {
-                        store_core(DZ, m, 1, z8, X_LO);
+                            for (int o = 16; o > 0; o >>= 1) sred += __shfl_xor_sync(0xffffffffu, sred, o);
+                            if (lane == 0 && sred != 0.f) red_add(GA + p.sdf[2].b_off, sred);
+                        } else if (part == 1) {
+                            store_core(DZ2, m, 1, z8, 4096);
+                        }
                     }
-                    signal_z(); wait_acc(); ep_mask(X1, GA + p.sdf[1].b_off, inv_scale);
-                    signal_z(); wait_acc(); ep_mask(X0, GA + p.sdf[0].b_off, inv_scale);
+                    signal_z(); wait_acc(); ep_mask(X0, csb + 64);
                     signal_z(); wait_acc();
                     float gt0, gt1;
                     ep_ds0(spt, gpt, inv_scale, gt0, gt1);
@@ -810,18 +865,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
                     tc_fence_before();
                     bar_workers();
                     grid_bwd_runs(gs, spt, G, gr.g_emb_sdf, gpt, inv_scale, j * TM, tid);
-                    bar_workers();
-                    if (tid < TM) {
-                        const int Q = j * TM + tid, s = Q / 6, q = Q - s * 6;
-                        const int axis = q >> 1;
-                        const float e = (q & 1) ? -FD_EPS : FD_EPS;
-#pragma unroll
-                        for (int a = 0; a < 3; a++) {
-                            float v = pt[a * TM + s];
-                            if (a == axis) v = __fadd_rn(v, e);
-                            if (v >= -p.bound && v <= p.bound) atomicAdd(gdst + a * TM + s, gpt[a * TM + tid]);   // clamp derivative
-                        }
-                    }
                     bar_workers();
                 }
             }
@@ -836,6 +879,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
                 flush_acc(320, p.color[0], 0, 64, 64, inv_scale);
                 flush_acc(384, p.color[1], 0, 64, 64, inv_scale);
                 flush_acc(448, p.color[2], 0, 64, 3, inv_scale);
+            }
+            if (tid < 256) {      // bias gradients accumulated over the tile: sdf1 | sdf0 | col1 | col0
+                const float sv = csb[tid];
+                if (sv != 0.f) {
+                    const uint32_t boff = (tid < 64) ? p.sdf[1].b_off : (tid < 128 ? p.sdf[0].b_off : (tid < 192 ? p.color[1].b_off : p.color[0].b_off));
+                    red_add(GA + boff + (tid & 63), sv * inv_scale);
+                }
             }
             tc_fence_before();
             bar_workers();

@@ -42,7 +42,8 @@ struct Smem {
     static constexpr int ST = SQ + 6 * 512;
     static constexpr int SALB = ST + 512;                    // [3][128]
     static constexpr int STQ = SALB + 3 * 512;               // [2][128] per-row topo of an FD sub-tile
-    static constexpr int OPS = STQ + 2 * 512;                // Op[MAX_OPS]
+    static constexpr int PSUM = STQ + 2 * 512;               // [2][128] partial dot products of the FD row-0 shortcut
+    static constexpr int OPS = PSUM + 2 * 512;               // Op[MAX_OPS]
     static constexpr int BAR = OPS + MAX_OPS * 12;           // mbarriers (8-byte aligned)
     static constexpr int TMEMH = BAR + 8 * (2 * NSTAGE + 2);
     static constexpr int TOTAL = TMEMH + 16;
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
     float* st = reinterpret_cast<float*>(smem + Smem::ST);
     float* salb = reinterpret_cast<float*>(smem + Smem::SALB);
     float* stq = reinterpret_cast<float*>(smem + Smem::STQ);
+    float* psum = reinterpret_cast<float*>(smem + Smem::PSUM);
     Op* ops = reinterpret_cast<Op*>(smem + Smem::OPS);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BAR);
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + Smem::TMEMH);
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
             if (flags & MB_F_COLOR) { push(15, 64); push(16, 64); push(17, 16); }
         }
         if (flags & MB_F_FD)
-            for (int q = 0; q < 6; q++) { push(12, 64); push(13, 64); push(14, 16); }
+            for (int q = 0; q < 6; q++) { push(12, 64); push(13, 64); }      // layer 2 (output row 0 only) is a dot product in the epilogue
         n_ops_s = n;
         for (int i = 0; i < NSTAGE; i++) { mbar_init(c.full + i, 1); mbar_init(c.empty + i, 1); }
         mbar_init(c.acc_ready, 1);
@@ -386,18 +388,26 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
                     epilogue_hidden<64>(c, AR + p.sdf[0].b_off, m, wg, warp_q);
                     signal_a(c);
                     wait_acc(c);
-                    epilogue_hidden<64>(c, AR + p.sdf[1].b_off, m, wg, warp_q);
-                    signal_a(c);
-                    wait_acc(c);
-                    if (wg == 0) {
-                        float v[16];
-                        tmem_ld16(c.tmem + ((uint32_t)(warp_q * 32) << 16), v);
-                        const int Q = j * TM + m, s = Q / 6, q = Q - s * 6;
-                        sq[q * TM + s] = v[0] + __ldg(AR + p.sdf[2].b_off);
+                    {
+                        // layer-1 epilogue fused with layer 2: an FD query only needs output row 0 (the sdf), i.e. the dot product
+                        // of relu(acc + b1) with W2[0, :] -- exact fp32 FMAs, no third MMA round trip, no operand re-split
+                        float v[32];
+                        tmem_ld32(c.tmem + ((uint32_t)(warp_q * 32) << 16) + wg * 32, v);
+                        const float* b1 = AR + p.sdf[1].b_off + wg * 32;
+                        const float* w2 = AR + p.sdf[2].w_off + wg * 32;          // W[n = 0][k], n-major slot
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; i++) acc = __fmaf_rn(fmaxf(v[i] + __ldg(b1 + i), 0.f), __ldg(w2 + i), acc);
+                        psum[wg * TM + m] = acc;
                     }
                     tc_fence_before();
                     bar_workers();
+                    if (tid < TM) {
+                        const int Q = j * TM + tid, s = Q / 6, q = Q - s * 6;
+                        sq[q * TM + s] = __fadd_rn(__fadd_rn(psum[tid], psum[TM + tid]), __ldg(AR + p.sdf[2].b_off));
+                    }
                 }
+                bar_workers();
             }
             // ---- per-sample outputs ----
             if (tid < nv) {
