@@ -228,6 +228,19 @@ int mb_sdf_loss_forward(const float* t_starts, const float* t_ends, const int64_
 int mb_sdf_loss_backward(const float* t_starts, const float* t_ends, const int64_t* ray_indices, const float* depth, const float* mask,
                          const float* sdf, uint32_t M, float truncation, const float* g_out2, float* g_sdf, mb_stream_t stream);
 
+/* pose correction of a ray batch (models/model.py:335-346, models/pose.py:35-58): pose [F,6] = (Euler a,b,g, translation);
+ * rays_o_out = rays_o + t_f, rays_d_out = R_f rays_d.  Backward ACCUMULATES into g_pose [F,6] (caller zero-fills) and writes
+ * g_rays_o / g_rays_d (nullable). */
+int mb_pose_rays_forward(const float* pose, const int64_t* frame_ids, const float* rays_o, const float* rays_d, uint32_t N,
+                         float* rays_o_out, float* rays_d_out, mb_stream_t stream);
+int mb_pose_rays_backward(const float* pose, const int64_t* frame_ids, const float* rays_d, const float* g_o_out, const float* g_d_out,
+                          uint32_t N, float* g_pose, float* g_rays_o, float* g_rays_d, mb_stream_t stream);
+/* per-ray loss heads of a real view (morpheus.py:946-983): out1[0] += w_rgb*mse(image,gt_rgb) + w_mask*bce(clip(opacity),gt_mask)
+ * + w_depth*mse(depth*dm, gt_depth*dm); also writes the per-ray gradients of that scalar (g_image [N,3], g_opacity [N], g_depth [N]). */
+int mb_ray_loss(const float* image, const float* opacity, const float* depth, const float* gt_rgb, const float* gt_depth,
+                const float* gt_mask, const float* rays_o, const float* rays_d, uint32_t N, float w_rgb, float w_mask, float w_depth,
+                float* out1, float* g_image, float* g_opacity, float* g_depth, mb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

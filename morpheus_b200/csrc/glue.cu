@@ -193,6 +193,148 @@ __global__ void sdf_loss_bwd_kernel(const float* __restrict__ t0, const float* _
     g_sdf[i] = g_out[0] * dfs + g_out[1] * dsl;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// pose correction of a ray batch: scene_representation.pose_optimisation (models/model.py:335-346) with
+// PoseArray.get_rotation_matrices (models/pose.py:35-58): R columns c1, c2, c3 from the Euler angles (a, b, g) of the ray's
+// frame, o' = o + t_f, d'_i = sum_j d_j R[i][j].  Same operation order / roundings as the eager torch expression.
+struct PoseR { float R[3][3]; float ca, cb, cg, sa, sb, sg; };
+__device__ __forceinline__ PoseR pose_matrix(const float* __restrict__ pr) {
+    PoseR P;
+    P.ca = cosf(pr[0]); P.cb = cosf(pr[1]); P.cg = cosf(pr[2]);
+    P.sa = sinf(pr[0]); P.sb = sinf(pr[1]); P.sg = sinf(pr[2]);
+    const float ca = P.ca, cb = P.cb, cg = P.cg, sa = P.sa, sb = P.sb, sg = P.sg;
+    P.R[0][0] = __fmul_rn(ca, cb); P.R[1][0] = __fmul_rn(sa, cb); P.R[2][0] = -sb;
+    P.R[0][1] = __fsub_rn(__fmul_rn(__fmul_rn(ca, sb), sg), __fmul_rn(sa, cg));
+    P.R[1][1] = __fadd_rn(__fmul_rn(__fmul_rn(sa, sb), sg), __fmul_rn(ca, cg));
+    P.R[2][1] = __fmul_rn(cb, sg);
+    P.R[0][2] = __fadd_rn(__fmul_rn(__fmul_rn(ca, sb), cg), __fmul_rn(sa, sg));
+    P.R[1][2] = __fsub_rn(__fmul_rn(__fmul_rn(sa, sb), cg), __fmul_rn(ca, sg));
+    P.R[2][2] = __fmul_rn(cb, cg);
+    return P;
+}
+
+__global__ void pose_rays_fwd_kernel(const float* __restrict__ pose, const int64_t* __restrict__ ids, const float* __restrict__ o,
+                                     const float* __restrict__ d, uint32_t N, float* __restrict__ o2, float* __restrict__ d2) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float* pr = pose + ids[i] * 6;
+    const PoseR P = pose_matrix(pr);
+    const float dv[3] = {d[(size_t)i * 3], d[(size_t)i * 3 + 1], d[(size_t)i * 3 + 2]};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        o2[(size_t)i * 3 + a] = __fadd_rn(o[(size_t)i * 3 + a], pr[3 + a]);
+        d2[(size_t)i * 3 + a] = __fadd_rn(__fadd_rn(__fmul_rn(dv[0], P.R[a][0]), __fmul_rn(dv[1], P.R[a][1])), __fmul_rn(dv[2], P.R[a][2]));
+    }
+}
+
+// g_pose[f][0..2] += sum_ij g_d2[i] d[j] dR[i][j]/d(angle), g_pose[f][3..5] += g_o2 ; g_o = g_o2, g_d[j] = sum_i g_d2[i] R[i][j]
+__global__ void pose_rays_bwd_kernel(const float* __restrict__ pose, const int64_t* __restrict__ ids, const float* __restrict__ d,
+                                     const float* __restrict__ g_o2, const float* __restrict__ g_d2, uint32_t N, float* __restrict__ g_pose,
+                                     float* __restrict__ g_o, float* __restrict__ g_d) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    float gp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int64_t f = -1;
+    if (i < N) {
+        f = ids[i];
+        const PoseR P = pose_matrix(pose + f * 6);
+        const float ca = P.ca, cb = P.cb, cg = P.cg, sa = P.sa, sb = P.sb, sg = P.sg;
+        const float dv[3] = {d[(size_t)i * 3], d[(size_t)i * 3 + 1], d[(size_t)i * 3 + 2]};
+        float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};
+        if (g_o2) { go[0] = g_o2[(size_t)i * 3]; go[1] = g_o2[(size_t)i * 3 + 1]; go[2] = g_o2[(size_t)i * 3 + 2]; }
+        if (g_d2) { gd[0] = g_d2[(size_t)i * 3]; gd[1] = g_d2[(size_t)i * 3 + 1]; gd[2] = g_d2[(size_t)i * 3 + 2]; }
+        // dR/da, dR/db, dR/dg (row i, column j)
+        const float Ra[3][3] = {{-sa * cb, -sa * sb * sg - ca * cg, -sa * sb * cg + ca * sg},
+                                {ca * cb, ca * sb * sg - sa * cg, ca * sb * cg + sa * sg},
+                                {0.f, 0.f, 0.f}};
+        const float Rb[3][3] = {{-ca * sb, ca * cb * sg, ca * cb * cg},
+                                {-sa * sb, sa * cb * sg, sa * cb * cg},
+                                {-cb, -sb * sg, -sb * cg}};
+        const float Rg[3][3] = {{0.f, ca * sb * cg + sa * sg, -ca * sb * sg + sa * cg},
+                                {0.f, sa * sb * cg - ca * sg, -sa * sb * sg - ca * cg},
+                                {0.f, cb * cg, -cb * sg}};
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float gR = gd[r] * dv[c];
+                gp[0] += gR * Ra[r][c];
+                gp[1] += gR * Rb[r][c];
+                gp[2] += gR * Rg[r][c];
+            }
+        gp[3] = go[0]; gp[4] = go[1]; gp[5] = go[2];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (g_o) g_o[(size_t)i * 3 + c] = go[c];
+            if (g_d) g_d[(size_t)i * 3 + c] = gd[0] * P.R[0][c] + gd[1] * P.R[1][c] + gd[2] * P.R[2][c];
+        }
+    }
+    // rays of a batch normally share one frame: reduce over the warp when they do
+    const int64_t f0 = __shfl_sync(0xffffffffu, f, 0);
+    const bool uniform = __all_sync(0xffffffffu, f == f0 || f < 0);
+    if (uniform) {
+#pragma unroll
+        for (int o_ = 16; o_ > 0; o_ >>= 1)
+#pragma unroll
+            for (int c = 0; c < 6; c++) gp[c] += __shfl_xor_sync(0xffffffffu, gp[c], o_);
+        if (lane == 0 && f0 >= 0)
+#pragma unroll
+            for (int c = 0; c < 6; c++) atomicAdd(g_pose + f0 * 6 + c, gp[c]);
+    } else if (f >= 0) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) atomicAdd(g_pose + f * 6 + c, gp[c]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-ray loss heads of a real view (morpheus.py:946-983): w_rgb * mse(image, gt) + w_mask * bce(clip(opacity), mask)
+// + w_depth * mse(depth * dm, gt_depth * dm), dm = (gt_depth > 0) & (|o + gt_depth d| <= 1.1) & (mask > .5).
+// One launch: out[0] += weighted loss; the per-ray gradients (already weighted, for d(loss) = 1) are stored for the backward.
+__global__ void ray_loss_kernel(const float* __restrict__ image, const float* __restrict__ opacity, const float* __restrict__ depth,
+                                const float* __restrict__ gt_rgb, const float* __restrict__ gt_depth, const float* __restrict__ gt_mask,
+                                const float* __restrict__ rays_o, const float* __restrict__ rays_d, uint32_t N, float w_rgb, float w_mask,
+                                float w_depth, float* __restrict__ out, float* __restrict__ g_image, float* __restrict__ g_opacity,
+                                float* __restrict__ g_depth) {
+    float acc = 0.f;
+    const float inv_n = 1.0f / (float)N, inv_3n = 1.0f / (3.0f * (float)N);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        float l = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float df = image[(size_t)i * 3 + c] - gt_rgb[(size_t)i * 3 + c];
+            l += w_rgb * df * df * inv_3n;
+            g_image[(size_t)i * 3 + c] = w_rgb * 2.f * df * inv_3n;
+        }
+        const float m = gt_mask[i], op = opacity[i];
+        const float x = fminf(fmaxf(op, 1e-5f), 1.0f - 1e-5f);
+        l += -w_mask * (m * fmaxf(logf(x), -100.f) + (1.f - m) * fmaxf(logf(1.f - x), -100.f)) * inv_n;
+        g_opacity[i] = (op >= 1e-5f && op <= 1.0f - 1e-5f) ? w_mask * (x - m) / fmaxf((1.f - x) * x, 1e-12f) * inv_n : 0.f;
+        const float gd = gt_depth[i];
+        float px[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) px[c] = rays_o[(size_t)i * 3 + c] + gd * rays_d[(size_t)i * 3 + c];
+        const float nrm = sqrtf(px[0] * px[0] + px[1] * px[1] + px[2] * px[2]);
+        const float dm = (gd > 0.f && nrm <= 1.1f && m > 0.5f) ? 1.f : 0.f;
+        const float dd = depth[i] * dm - gd * dm;
+        l += w_depth * dd * dd * inv_n;
+        g_depth[i] = w_depth * 2.f * dd * dm * inv_n;
+        acc += l;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ float sa[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) sa[w] = acc;
+    __syncthreads();
+    if (w == 0) {
+        acc = lane < (int)(blockDim.x >> 5) ? sa[lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) atomicAdd(out, acc);
+    }
+}
+
 }  // namespace mb
 
 extern "C" int mb_ray_points_forward(const float* rays_o, const float* rays_d, const int64_t* ray_indices, const float* t_starts,
@@ -245,4 +387,36 @@ extern "C" int mb_sdf_loss_backward(const float* t_starts, const float* t_ends, 
     if (M == 0) return MB_OK;
     sdf_loss_bwd_kernel<<<div_up(M, 256), 256, 0, (cudaStream_t)stream>>>(t_starts, t_ends, ray_indices, depth, mask, sdf, M, truncation, g_out2, g_sdf);
     return check_launch("sdf_loss_backward");
+}
+
+extern "C" int mb_pose_rays_forward(const float* pose, const int64_t* frame_ids, const float* rays_o, const float* rays_d, uint32_t N,
+                                    float* rays_o_out, float* rays_d_out, mb_stream_t stream) {
+    using namespace mb;
+    if (N == 0) return MB_OK;
+    if (!pose || !frame_ids || !rays_o || !rays_d || !rays_o_out || !rays_d_out) { set_error("pose_rays_forward: null argument"); return MB_EINVAL; }
+    pose_rays_fwd_kernel<<<div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(pose, frame_ids, rays_o, rays_d, N, rays_o_out, rays_d_out);
+    return check_launch("pose_rays_forward");
+}
+
+extern "C" int mb_pose_rays_backward(const float* pose, const int64_t* frame_ids, const float* rays_d, const float* g_o_out, const float* g_d_out,
+                                     uint32_t N, float* g_pose, float* g_rays_o, float* g_rays_d, mb_stream_t stream) {
+    using namespace mb;
+    if (N == 0) return MB_OK;
+    if (!pose || !frame_ids || !rays_d || !g_pose) { set_error("pose_rays_backward: null argument"); return MB_EINVAL; }
+    pose_rays_bwd_kernel<<<div_up(N, 128), 128, 0, (cudaStream_t)stream>>>(pose, frame_ids, rays_d, g_o_out, g_d_out, N, g_pose, g_rays_o, g_rays_d);
+    return check_launch("pose_rays_backward");
+}
+
+extern "C" int mb_ray_loss(const float* image, const float* opacity, const float* depth, const float* gt_rgb, const float* gt_depth,
+                           const float* gt_mask, const float* rays_o, const float* rays_d, uint32_t N, float w_rgb, float w_mask, float w_depth,
+                           float* out1, float* g_image, float* g_opacity, float* g_depth, mb_stream_t stream) {
+    using namespace mb;
+    if (!image || !opacity || !depth || !gt_rgb || !gt_depth || !gt_mask || !rays_o || !rays_d || !out1 || !g_image || !g_opacity || !g_depth) {
+        set_error("ray_loss: null argument");
+        return MB_EINVAL;
+    }
+    if (N == 0) return MB_OK;
+    ray_loss_kernel<<<min(div_up(N, 256), (uint32_t)mb_sm_count()), 256, 0, (cudaStream_t)stream>>>(image, opacity, depth, gt_rgb, gt_depth, gt_mask, rays_o, rays_d,
+                                                                                                     N, w_rgb, w_mask, w_depth, out1, g_image, g_opacity, g_depth);
+    return check_launch("ray_loss");
 }

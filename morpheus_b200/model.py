@@ -221,6 +221,36 @@ def get_encoder(encoding, input_dim=3, multires=6, num_levels=16, level_dim=2, b
     return enc, enc.output_dim
 
 
+class _PoseRays(torch.autograd.Function):
+    """scene_representation.pose_optimisation (models/model.py:335-346) in one launch (and one backward launch) instead of
+    ~35 eager ops + their autograd nodes; same operation order as the torch expression (bit-identical forward)."""
+
+    @staticmethod
+    def forward(ctx, pose, rays_o, rays_d, frame_ids):
+        rays_o, rays_d = rays_o.contiguous().float(), rays_d.contiguous().float()
+        frame_ids = frame_ids.contiguous().long()
+        N = rays_o.shape[0]
+        o2, d2 = torch.empty_like(rays_o), torch.empty_like(rays_d)
+        check(_lib.lib().mb_pose_rays_forward(ptr(pose.detach()), ptr(frame_ids), ptr(rays_o), ptr(rays_d), N, ptr(o2), ptr(d2), stream()),
+              'pose_rays_forward')
+        ctx.save_for_backward(pose, rays_d, frame_ids)
+        ctx.set_materialize_grads(False)
+        return o2, d2
+
+    @staticmethod
+    def backward(ctx, g_o2, g_d2):
+        pose, rays_d, frame_ids = ctx.saved_tensors
+        N = rays_d.shape[0]
+        g_pose = torch.zeros_like(pose)
+        g_o = torch.empty_like(rays_d) if ctx.needs_input_grad[1] else None
+        g_d = torch.empty_like(rays_d) if ctx.needs_input_grad[2] else None
+        g_o2 = g_o2.contiguous().float() if g_o2 is not None else None
+        g_d2 = g_d2.contiguous().float() if g_d2 is not None else None
+        check(_lib.lib().mb_pose_rays_backward(ptr(pose.detach()), ptr(frame_ids), ptr(rays_d), ptr(g_o2), ptr(g_d2), N, ptr(g_pose), ptr(g_o), ptr(g_d),
+                                               stream()), 'pose_rays_backward')
+        return g_pose, g_o, g_d, None
+
+
 # ------------------------------------------------------------------------------------------------
 # parameter arena: weight_norm + transpose + pad of the 18 dense layers in ONE launch (and one backward launch)
 # ------------------------------------------------------------------------------------------------
@@ -554,6 +584,8 @@ class scene_representation(nn.Module):
     def pose_optimisation(self, rays_o, rays_d, frame_ids):
         """model.py:335-346"""
         frame_ids = frame_ids.squeeze()
+        if rays_o.is_cuda and rays_o.dim() == 2 and frame_ids.dim() == 1 and frame_ids.shape[0] == rays_o.shape[0]:
+            return _PoseRays.apply(self.pose_array.data, rays_o, rays_d, frame_ids)
         R = self.pose_array.get_rotation_matrices(frame_ids)
         tr = self.pose_array.get_translations(frame_ids)
         return rays_o + tr, torch.sum(rays_d[..., None, :] * R, -1)

@@ -21,9 +21,50 @@ DEFAULT_TRAIN_CFG = {  # configs/snoopy.yaml:40-94 (only what the step reads)
 }
 
 
+class _RayLoss(torch.autograd.Function):
+    """rgb MSE + mask BCE + masked depth MSE of get_real_view_render_loss (morpheus.py:946-983) in one launch; the kernel also
+    emits the per-ray gradients, so the backward is three scalings."""
+
+    @staticmethod
+    def forward(ctx, image, opacity, depth, gt_rgb, gt_depth, gt_mask, rays_o, rays_d, w_rgb, w_mask, w_depth):
+        image, opacity, depth = image.contiguous().float(), opacity.contiguous().float(), depth.contiguous().float()
+        N = opacity.shape[0]
+        out = torch.zeros(1, device=image.device, dtype=torch.float32)
+        g_i, g_o, g_d = torch.empty_like(image), torch.empty_like(opacity), torch.empty_like(depth)
+        check(_lib.lib().mb_ray_loss(ptr(image), ptr(opacity), ptr(depth), ptr(gt_rgb.contiguous().float()), ptr(gt_depth.contiguous().float()),
+                                     ptr(gt_mask.contiguous().float()), ptr(rays_o.contiguous().float()), ptr(rays_d.contiguous().float()), N,
+                                     C.c_float(w_rgb), C.c_float(w_mask), C.c_float(w_depth), ptr(out), ptr(g_i), ptr(g_o), ptr(g_d), stream()),
+              'ray_loss')
+        ctx.save_for_backward(g_i, g_o, g_d)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        g_i, g_o, g_d = ctx.saved_tensors
+        return (g_i * g, g_o * g, g_d * g) + (None,) * 8
+
+
 def real_view_loss(out, batch, model, tr):
-    """rgb MSE x5 + mask BCE x.5 + masked depth MSE x.1 (morpheus.py:946-983) + sdf band loss x10 (:991-992)
+    """rgb MSE x5 + mask BCE x.5 + masked depth MSE x.1 (morpheus.py:946-983, one fused launch) + sdf band loss x10 (:991-992)
     + normal_smooth_3d x.1 + code_reg x.5 + beta x.1 (:1116-1142)."""
+    pred_rgb = out['image'].reshape(-1, 3)
+    pred_depth = out['depth'].reshape(-1)
+    pred_mask = out['weights_sum'].reshape(-1)
+    gt_depth = batch['depth'].reshape(-1)
+    loss = _RayLoss.apply(pred_rgb, pred_mask, pred_depth, batch['rgb'], gt_depth, batch['mask'].reshape(-1), batch['rays_o'].reshape(-1, 3),
+                          batch['rays_d'].reshape(-1, 3), float(tr['rgb_weight']), float(tr['mask_weight']), float(tr['depth_weight']))
+    if 'sdf_loss' in out:
+        loss = loss + tr['sdf_weight'] * out['sdf_loss'] + tr['fs_weight'] * out['fs_loss']
+    if 'loss_normal_perturb' in out:
+        loss = loss + tr['normal_smooth_3d'] * out['loss_normal_perturb']
+    if 'loss_code' in out:
+        loss = loss + tr['code_reg'] * out['loss_code']
+    loss = loss + tr['beta_weight'] * torch.mean(model.sdf2density.get_beta())
+    return loss
+
+
+def real_view_loss_torch(out, batch, model, tr):
+    """the same loss as eager torch ops (reference formulation; used by the parity tests)"""
     pred_rgb = out['image'].reshape(-1, 3)
     pred_depth = out['depth'].reshape(-1)
     pred_mask = out['weights_sum'].reshape(-1)

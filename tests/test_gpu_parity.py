@@ -607,3 +607,49 @@ def test_ray_points_and_sdf_loss_match_torch(dev):
     ga = torch.autograd.grad(2.0 * fs + 3.0 * sl, sdf)[0]
     gb = torch.autograd.grad(2.0 * fs_ref + 3.0 * sl_ref, sdf)[0]
     assert rel_l2(cpu(ga), cpu(gb)) < 1e-5
+
+
+def test_pose_rays_and_ray_loss_match_torch(dev):
+    """fused pose correction (models/model.py:335-346) and loss heads (morpheus.py:946-983) vs their eager torch forms"""
+    from morpheus_b200 import train as mtrain
+    from oracle.fields import init_reference_like_state
+    sd = init_reference_like_state(200, seed=2, randomize=True, emb_scale=0.02)
+    m = make_model(sd, 1.0, dev).train()
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        m.pose_array.data.copy_((torch.randn(200, 6, generator=g) * 0.05).to(dev))
+    N = 777
+    o = torch.randn(N, 3, generator=g).to(dev).requires_grad_(True)
+    d = torch.randn(N, 3, generator=g).to(dev).requires_grad_(True)
+    ids = torch.randint(0, 200, (N, 1), generator=g).to(dev)
+    ids[:400] = 17                                  # warp-uniform and mixed warps
+    o2, d2 = m.pose_optimisation(o, d, ids)
+    R = m.pose_array.get_rotation_matrices(ids.squeeze())
+    o2r, d2r = o + m.pose_array.get_translations(ids.squeeze()), torch.sum(d[..., None, :] * R, -1)
+    assert torch.equal(o2, o2r)
+    assert float((d2 - d2r).abs().max()) < 1e-6
+    w1, w2 = torch.randn(N, 3, generator=g).to(dev), torch.randn(N, 3, generator=g).to(dev)
+    ga = torch.autograd.grad((o2 * w1).sum() + (d2 * w2).sum(), [m.pose_array.data, o, d])
+    gb = torch.autograd.grad((o2r * w1).sum() + (d2r * w2).sum(), [m.pose_array.data, o, d])
+    for a, b in zip(ga, gb):
+        assert rel_l2(cpu(a), cpu(b)) < 1e-5
+    # loss heads
+    tr = dict(mtrain.DEFAULT_TRAIN_CFG)
+    img = torch.rand(N, 3, generator=g).to(dev).requires_grad_(True)
+    dep = (torch.rand(N, generator=g) * 3).to(dev).requires_grad_(True)
+    opa = torch.rand(N, generator=g)
+    opa[:5] = 0.0
+    opa[5:9] = 1.0
+    opa = opa.to(dev).requires_grad_(True)
+    gt_depth = torch.rand(N, generator=g) * 2
+    gt_depth[::5] = 0.0
+    batch = {'rgb': torch.rand(N, 3, generator=g).to(dev), 'depth': gt_depth.to(dev), 'mask': (torch.rand(N, generator=g) > 0.4).float().to(dev),
+             'rays_o': (torch.randn(N, 3, generator=g) * 0.3).to(dev), 'rays_d': (torch.randn(N, 3, generator=g) * 0.3).to(dev)}
+    out = {'image': img, 'depth': dep, 'weights_sum': opa}
+    la = mtrain.real_view_loss(out, batch, m, tr)
+    lb = mtrain.real_view_loss_torch(out, batch, m, tr)
+    assert abs(float(la) - float(lb)) < 1e-5 * max(1.0, abs(float(lb)))
+    ga = torch.autograd.grad(la, [img, dep, opa])
+    gb = torch.autograd.grad(lb, [img, dep, opa])
+    for a, b in zip(ga, gb):
+        assert rel_l2(cpu(a), cpu(b)) < 1e-5
