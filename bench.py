@@ -160,6 +160,8 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's own 'NCCL version ...' banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group('nccl', device_id=dev)
     model = make_state().to(dev).train()
     state_for_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()} if rank == 0 else None
@@ -267,19 +269,26 @@ def main():
         }
         engine = {k: 'tcgen05 (3x fp16 split)' for k in flops}
         engine['field_bwd_main'] = engine['field_bwd_aux'] = 'fp32 SIMT'
+        # per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the `ncu --set full` captures summarised under
+        # profiles/ (tools/summarize_profiles.py traffic): same M and flags as the bench's main launches
+        traffic = {}
+        tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tp):
+            traffic = json.load(open(tp))
         rooflines = []
         for name, fl in flops.items():
             if name in kern:
                 ach = fl / (kern[name]['avg_ms'] * 1e-3) / 1e12
                 rooflines.append({'kernel': name, 'engine': engine[name], 'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s',
-                                  'frac': ach / tf_peak, 'traffic': None, 'avg_launch_ms': kern[name]['avg_ms'], 'launches_timed': kern[name]['n'],
+                                  'frac': ach / tf_peak, 'traffic': traffic.get(name), 'avg_launch_ms': kern[name]['avg_ms'], 'launches_timed': kern[name]['n'],
                                   'algorithmic_flops_per_launch': fl})
         rooflines.sort(key=lambda r: -r['avg_launch_ms'])
         roof = None
         if rooflines:
             roof = dict(rooflines[0], peak_source=which,
-                        note='dominant kernel by measured time; fp32-parity engine: tensor-core kernels spend 3 MMAs per product (fp16 hi/lo split), '
-                             'SIMT kernels are bounded by the 72 TFLOP/s fp32 FMA pipe; all kernels in "rooflines"')
+                        note='dominant kernel by measured time; achieved = ALGORITHMIC flops (2/MAC, backward = 2x forward, recompute and the 3x fp16 hi/lo '
+                             'split of every product not counted) / CUDA-event launch time; the kernel is bound by L2 gather/scatter latency and CUDA-core '
+                             'epilogues, not by the tensor pipe (5 % active, profiles/); traffic = DRAM bytes per launch from ncu; all kernels in "rooflines"')
         launches = sum(v['n'] for v in kern.values()) // max(kern_steps, 1) if kern else None
         cpu_val = None
         if args.cpu_baseline_steps > 0:
