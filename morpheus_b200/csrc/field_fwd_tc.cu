@@ -12,6 +12,8 @@
 //   * 3 MMAs per K step (hi*hi + hi*lo + lo*hi) keep ~2^-22 relative accuracy (fp32 parity, see tc_common.cuh);
 //   * warp roles: warps 0-7 build inputs (hash-grid gathers, encodings) and run epilogues, warp 8 lane 0 issues the
 //     bulk copies and the MMAs; hand-offs are mbarriers (a_ready: 256 arrivals, acc_ready / empty[]: tcgen05.commit).
+#include <stdlib.h>
+
 #include "field_common.cuh"
 #include "tc_common.cuh"
 #include "tc_field.cuh"
@@ -517,7 +519,9 @@ extern "C" int mb_field_forward_tc(const mb_field_params* p, const mb_field_io* 
         attr_set = true;
     }
     const uint32_t n_tiles = div_up(io->M, tc::TM);
-    const uint32_t grid = min(n_tiles, (uint32_t)mb_sm_count() * 2u);
+    static int ctas_per_sm = 0;      // MB_FWD_CTAS_PER_SM=1: occupancy experiment (default 2 resident CTAs per SM)
+    if (!ctas_per_sm) { const char* e = getenv("MB_FWD_CTAS_PER_SM"); ctas_per_sm = (e && atoi(e) == 1) ? 1 : 2; }
+    const uint32_t grid = min(n_tiles, (uint32_t)mb_sm_count() * (uint32_t)ctas_per_sm);
     tc::field_fwd_tc_kernel<<<grid, tc::NTHREADS, smem, (cudaStream_t)stream>>>(*p, *io, (const uint8_t*)tc_weights, tc_off, (uint8_t*)stash);
     return check_launch("field_forward_tc");
 }
