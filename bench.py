@@ -143,6 +143,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-baseline-steps', type=int, default=2)
     ap.add_argument('--no-graph', action='store_true', help='run the step eagerly instead of replaying the captured CUDA graph')
+    ap.add_argument('--full-step', action='store_true', help='add the SURVEY 8f rank-1 terms (normal smoothness on 11 band points/ray, '
+                    'surface-point SDF/colour) to the step: the complete real-view iteration of morpheus.py:1147-1236')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3 if args.impl == 'ours' else 1)
     rank = int(os.environ.get('RANK', '0'))
@@ -165,7 +167,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     model = make_state().to(dev).train()
     state_for_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()} if rank == 0 else None
-    tr = dict(mtrain.DEFAULT_TRAIN_CFG)
+    tr = dict(mtrain.FULL_TRAIN_CFG if args.full_step else mtrain.DEFAULT_TRAIN_CFG)
     cfg = dict(CONFIG, train=tr)
     R = Renderer(model, OccGridEstimator(torch.tensor([-1.01] * 3 + [1.01] * 3), 128).to(dev), cfg, NUM_FRAMES, uniform_samples=N_SAMPLES)
     R.world_size = world
@@ -277,7 +279,7 @@ def main():
             traffic = json.load(open(tp))
         rooflines = []
         for name, fl in flops.items():
-            if name in kern:
+            if name in kern and not args.full_step:      # (--full-step adds launches of other sizes under the same names)
                 ach = fl / (kern[name]['avg_ms'] * 1e-3) / 1e12
                 rooflines.append({'kernel': name, 'engine': engine[name], 'bound': 'tensor', 'achieved': ach, 'peak': tf_peak, 'unit': 'TFLOP/s',
                                   'frac': ach / tf_peak, 'traffic': traffic.get(name), 'avg_launch_ms': kern[name]['avg_ms'], 'launches_timed': kern[name]['n'],
@@ -296,7 +298,7 @@ def main():
             cpu_val = 64 / (sum(times) / len(times))
         line = {'metric': 'rays_per_sec_train_step', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': dict(workload_config(world), cuda_graph=(not args.no_graph)), 'clocks': clocks,
+                'config': dict(workload_config(world), cuda_graph=(not args.no_graph), full_step=bool(args.full_step)), 'clocks': clocks,
                 'e2e': {'value': e2e_val, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
                 'gpu_launches': launches, 'kernels': kern, 'final_loss': last_loss,
                 'roofline': roof, 'rooflines': rooflines,

@@ -7,7 +7,10 @@ Launch count per real-view training step: sampler (2) + field forward (1) + comp
 perturbed-normal query (1) forward, and as many backward -- versus ~300 eager kernels in the
 reference.
 """
+import math
+
 import torch
+import torch.nn.functional as F
 
 from . import _lib
 from . import nerfacc_compat as nerfacc
@@ -158,6 +161,38 @@ class Renderer:
             return self.model.density(x, rays_t, allow_shape=True, cano=cano, return_color=False)['sigma'] * self.config['render']['step_size']
         self.occupancy_grid.update_every_n_steps(step=step, occ_eval_fn=occ_eval_fn)
 
+    @staticmethod
+    def get_ortho_normal_dir(normals, phi=None):
+        """morpheus.py:518-528: a random unit direction orthogonal to the normal (`phi` [.., 1] in [0, 2 pi) injects the draw)"""
+        n = F.normalize(normals, dim=-1)
+        u = F.normalize(torch.stack([n[..., 1], -n[..., 0], torch.zeros_like(n[..., 2])], dim=-1), dim=-1)   # n[..., [1,0,2]] * (1,-1,0), capture-safe
+        v = torch.cross(n, u, dim=-1)
+        if phi is None:
+            phi = torch.rand(list(normals.shape[:-1]) + [1], device=normals.device) * 2. * math.pi
+        return torch.cos(phi) * u + torch.sin(phi) * v
+
+    def get_normal_smoothness_loss(self, rays_o, rays_d, rays_t, depth, *, trunc_noise=None, phi=None):
+        """morpheus.py:530-556 (L_smooth in observation space): 11 points per ray in a band around the rendered depth, the
+        fused `normal(x, t)` query (deform + topology nets + 6 warped SDF queries, ONE launch) at each point and at a point
+        displaced by smoothness_std along a random tangent, mean squared normal difference.  The reference drops the points
+        with |x| >= 1.1 by boolean indexing (a data-dependent shape: host sync, not graph-capturable); here every point is
+        evaluated and the dropped ones get weight 0 -- the same mean over the kept points."""
+        tr = self.config['train']
+        n_pts = int(tr['trunc'] * 100 + 1)
+        dev = rays_o.device
+        trunc_normal = torch.linspace(-0.5 * tr['trunc'], 0.5 * tr['trunc'], n_pts, device=dev)
+        if trunc_noise is None:
+            trunc_noise = torch.rand_like(trunc_normal)
+        trunc_normal = trunc_normal + 0.01 * trunc_noise
+        depth = depth.reshape(1, -1)
+        surf_pts = ((depth + trunc_normal[:, None])[..., None] * rays_d[None, ...] + rays_o[None, ...]).reshape(-1, 3)
+        surf_t = rays_t.reshape(1, -1, 1).repeat(n_pts, 1, 1).reshape(-1, 1)
+        keep = (torch.linalg.norm(surf_pts.detach(), ord=2, dim=-1) < 1.1).to(surf_pts.dtype)
+        n1, _ = self.model.normal(surf_pts, t=surf_t)
+        w = self.get_ortho_normal_dir(n1, phi)
+        n2, _ = self.model.normal(surf_pts + w * tr['smoothness_std'], t=surf_t)
+        return (torch.square(n1 - n2) * keep[:, None]).sum() / (3.0 * keep.sum().clamp(min=1.0))
+
     def render_rays(self, rays_o, rays_d, rays_t, rays_id, H=None, W=None, perturb=True, bg_color=None, ambient_ratio=1.0,
                     light_d=None, shading='albedo', real_view=True, cano=False, rays_depth=None, rays_mask=None,
                     optimize_pose=False, *, samples=None, perturb_noise=None, jitter=None):
@@ -229,6 +264,8 @@ class Renderer:
                 # morpheus.py:766-771: code(t), code(t - 1/F), code(t + 1/F) -- sampled in ONE batched call (same arithmetic per row)
                 codes = model.get_deform_code(torch.cat([ts, ts - 1 / self.num_frames, ts + 1 / self.num_frames], dim=0))
                 results['loss_code'] = torch.square(2 * codes[0:1] - codes[1:2] - codes[2:3]).mean()
+            if tr.get('normal_smoothness', 0) > 0:
+                results['normal_reg'] = self.get_normal_smoothness_loss(rays_o, rays_d, rays_t, depth)      # morpheus.py:778-785
             if rays_depth is not None:
                 if self.sdf_count_override is not None:
                     cnt = self.sdf_count_override

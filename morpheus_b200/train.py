@@ -18,7 +18,22 @@ DEFAULT_TRAIN_CFG = {  # configs/snoopy.yaml:40-94 (only what the step reads)
     'rgb_weight': 5.0, 'mask_weight': 0.5, 'depth_weight': 0.1, 'sdf_weight': 10.0, 'fs_weight': 0.0,
     'normal_smooth_3d': 0.1, 'smoothness_std': 0.005, 'topo_none': True, 'normal_dir': False, 'code_reg': 0.5,
     'beta_weight': 0.1, 'ori_weight': 0.01, 'trunc': 0.1, 'lr': 5e-4,
+    # SURVEY 8f rank 1 (off in the BASELINE cfg-2 'mode B' step; FULL_TRAIN_CFG switches them on with the shipped weights)
+    'normal_smoothness': 0.0, 'surf_sdf_weight': 0.0, 'surf_color_weight': 0.0,
 }
+FULL_TRAIN_CFG = dict(DEFAULT_TRAIN_CFG, normal_smoothness=0.4, surf_sdf_weight=10.0, surf_color_weight=5.0)   # configs/snoopy.yaml:70-74
+
+
+def surface_point_loss(model, batch, tr):
+    """get_real_view_point_loss, surface terms (morpheus.py:1005-1029): one fused density query (warp + SDF + colour) at the
+    back-projected depth points; SDF^2 averaged over the valid points, colour MSE over all points with invalid ones zeroed."""
+    gt_depth, gt_mask = batch['depth'].reshape(-1), batch['mask'].reshape(-1)
+    xyz = batch['rays_o'].reshape(-1, 3) + gt_depth[:, None] * batch['rays_d'].reshape(-1, 3)
+    dm = ((gt_depth > 0) & (xyz.norm(dim=-1) <= 1.1) & (gt_mask > 0.5)).float()
+    res = model.density(xyz, t=batch['rays_t'].reshape(-1, 1))
+    surf_sdf = tr['surf_sdf_weight'] * (res['sdf'].square() * dm).sum() / dm.sum().clamp(min=1.0)
+    surf_col = tr['surf_color_weight'] * F.mse_loss(res['albedo'] * dm[:, None], batch['rgb'] * dm[:, None])
+    return surf_sdf + surf_col
 
 
 class _RayLoss(torch.autograd.Function):
@@ -59,6 +74,10 @@ def real_view_loss(out, batch, model, tr):
         loss = loss + tr['normal_smooth_3d'] * out['loss_normal_perturb']
     if 'loss_code' in out:
         loss = loss + tr['code_reg'] * out['loss_code']
+    if 'normal_reg' in out:
+        loss = loss + tr['normal_smoothness'] * out['normal_reg']
+    if tr.get('surf_sdf_weight', 0) > 0:
+        loss = loss + surface_point_loss(model, batch, tr)
     loss = loss + tr['beta_weight'] * torch.mean(model.sdf2density.get_beta())
     return loss
 
@@ -80,6 +99,10 @@ def real_view_loss_torch(out, batch, model, tr):
         loss = loss + tr['normal_smooth_3d'] * out['loss_normal_perturb']
     if 'loss_code' in out:
         loss = loss + tr['code_reg'] * out['loss_code']
+    if 'normal_reg' in out:
+        loss = loss + tr['normal_smoothness'] * out['normal_reg']
+    if tr.get('surf_sdf_weight', 0) > 0:
+        loss = loss + surface_point_loss(model, batch, tr)
     loss = loss + tr['beta_weight'] * torch.mean(model.sdf2density.get_beta())
     return loss
 

@@ -653,3 +653,54 @@ def test_pose_rays_and_ray_loss_match_torch(dev):
     gb = torch.autograd.grad(lb, [img, dep, opa])
     for a, b in zip(ga, gb):
         assert rel_l2(cpu(a), cpu(b)) < 1e-5
+
+
+def test_normal_smoothness_and_surface_point_losses_vs_oracle(dev):
+    """get_normal_smoothness_loss (morpheus.py:530-556) and the surface-point terms of
+    get_real_view_point_loss (:1005-1029) on the fused normal(x, t) / density(x, t) queries vs the CPU oracle scene."""
+    import math
+    from morpheus_b200 import train as mtrain
+    from morpheus_b200.nerfacc_compat import OccGridEstimator
+    from morpheus_b200.render import Renderer
+    from oracle.fields import SceneOracle, init_reference_like_state
+    sd = init_reference_like_state(200, seed=21, randomize=True, emb_scale=0.3, sphere=True)
+    m = make_model(sd, 1.0, dev).train()
+    tr = dict(mtrain.FULL_TRAIN_CFG)
+    cfg = {'model': {'bg_radius': 1.4, 'activation': 'exp'}, 'render': {'step_size': 0.01}, 'train': tr}
+    R = Renderer(m, OccGridEstimator(torch.tensor([-1.01] * 3 + [1.01] * 3), 128).to(dev), cfg, 200)
+    g = torch.Generator().manual_seed(4)
+    N = 40
+    o = (torch.randn(N, 3, generator=g) * 0.2)
+    d = torch.nn.functional.normalize(torch.randn(N, 3, generator=g), dim=-1) * 0.5
+    depth = torch.rand(N, generator=g) * 1.5 + 0.2
+    depth[:4] = 5.0                                        # points outside the 1.1 sphere are dropped
+    t = torch.full((N, 1), 31.0 / 200)
+    noise = torch.rand(11, generator=g)
+    phi = torch.rand(11 * N, 1, generator=g) * 2 * math.pi
+    # oracle (CPU, eager torch, boolean indexing as the reference)
+    sc = SceneOracle({k: v.clone() for k, v in sd.items()}, 1.01, 200, 1.0)
+    oc, dc, depc = o.clone().requires_grad_(True), d.clone(), depth.clone().requires_grad_(True)
+    tn = torch.linspace(-0.05, 0.05, 11) + 0.01 * noise
+    pts = ((depc[None, :] + tn[:, None])[..., None] * dc[None] + oc[None]).view(-1, 3)
+    ts = t[None].repeat(11, 1, 1).view(-1, 1)
+    keep = torch.linalg.norm(pts, dim=-1) < 1.1
+    n1, _ = sc.normal(pts[keep], t=ts[keep])
+    w = Renderer.get_ortho_normal_dir(n1, phi[keep])
+    n2, _ = sc.normal(pts[keep] + w * tr['smoothness_std'], t=ts[keep])
+    ref = torch.mean(torch.square(n1 - n2))
+    g_ref = torch.autograd.grad(ref, [oc, depc])
+    og, dg = o.to(dev).requires_grad_(True), depth.to(dev).requires_grad_(True)
+    out = R.get_normal_smoothness_loss(og, d.to(dev), t.to(dev), dg, trunc_noise=noise.to(dev), phi=phi.to(dev))
+    g_out = torch.autograd.grad(out, [og, dg])
+    assert abs(float(out) - float(ref)) < 2e-3 * abs(float(ref)) + 1e-7, (float(out), float(ref))
+    for a, b in zip(g_out, g_ref):
+        assert rel_l2(cpu(a), b.numpy()) < 2e-2            # second differences of FD normals (eps 2e-3): ill-conditioned in fp32
+    # surface-point terms
+    batch = {'rays_o': o.to(dev), 'rays_d': d.to(dev), 'rays_t': t.to(dev), 'depth': depth.to(dev), 'mask': (torch.rand(N, generator=g) > 0.3).float().to(dev),
+             'rgb': torch.rand(N, 3, generator=g).to(dev)}
+    loss = mtrain.surface_point_loss(m, batch, tr)
+    xyz = o + depth[:, None] * d
+    dm = ((depth > 0) & (xyz.norm(dim=-1) <= 1.1) & (batch['mask'].cpu() > 0.5))
+    res = sc.density(xyz, t=t)
+    ref = 10.0 * torch.mean(torch.square(res['sdf'][dm])) + 5.0 * torch.nn.functional.mse_loss(res['albedo'] * dm[:, None].float(), batch['rgb'].cpu() * dm[:, None].float())
+    assert abs(float(loss) - float(ref)) < 1e-4 * abs(float(ref)) + 1e-7, (float(loss), float(ref))
