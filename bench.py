@@ -136,6 +136,7 @@ def workload_config(n_gpus):
 
 # ------------------------------------------------------------------------------------------------
 def main():
+    global N_RAYS
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -143,9 +144,11 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-baseline-steps', type=int, default=2)
     ap.add_argument('--no-graph', action='store_true', help='run the step eagerly instead of replaying the captured CUDA graph')
+    ap.add_argument('--rays', type=int, default=N_RAYS, help='global rays per step (BASELINE cfg-2: 4096; cfg-4 teddy shape: 8192)')
     ap.add_argument('--full-step', action='store_true', help='add the SURVEY 8f rank-1 terms (normal smoothness on 11 band points/ray, '
                     'surface-point SDF/colour) to the step: the complete real-view iteration of morpheus.py:1147-1236')
     args = ap.parse_args()
+    N_RAYS = args.rays
     args.warmup = max(args.warmup, 3 if args.impl == 'ours' else 1)
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
