@@ -161,6 +161,44 @@ class Renderer:
             return self.model.density(x, rays_t, allow_shape=True, cano=cano, return_color=False)['sigma'] * self.config['render']['step_size']
         self.occupancy_grid.update_every_n_steps(step=step, occ_eval_fn=occ_eval_fn)
 
+    # -- forward-only consumers -------------------------------------------------------------------
+    @torch.no_grad()
+    def sdf_volume(self, resolution=128, S=128, t=None, cano=False):
+        """The dense SDF grid `MorpheuS.export_mesh` feeds to marching cubes (morpheus.py:384-396): linspace(-1, 1, resolution)^3,
+        queried in S^3 blocks through the fused density launch (SDF only, no colour net).  -> [resolution]^3 fp32 on the device."""
+        dev = self.model.encoder.embeddings.device
+        vol = torch.empty(resolution, resolution, resolution, device=dev)
+        axis = torch.linspace(-1, 1, resolution, device=dev).split(S)
+        for xi, xs in enumerate(axis):
+            for yi, ys in enumerate(axis):
+                for zi, zs in enumerate(axis):
+                    xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing='ij')
+                    pts = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], dim=-1)
+                    val = self.model.density(pts, t=t, cano=cano, return_color=False)
+                    vol[xi * S: xi * S + len(xs), yi * S: yi * S + len(ys), zi * S: zi * S + len(zs)] = val['sdf'].reshape(len(xs), len(ys), len(zs))
+        return vol
+
+    @torch.no_grad()
+    def render_image(self, rays_o, rays_d, rays_t, rays_id, chunk=16384, **kw):
+        """eval-time render of a full view in ray chunks (morpheus.py:1238-1269 eval_step -> render_rays with perturb=False):
+        -> dict(image [N,3], depth [N], weights_sum [N,1])."""
+        was_training = self.model.training
+        self.model.eval()
+        try:
+            o, d = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
+            t, i = rays_t.reshape(-1, 1), rays_id.reshape(-1, 1)
+            outs = {'image': [], 'depth': [], 'weights_sum': []}
+            for a in range(0, o.shape[0], chunk):
+                r = self.render_rays(o[a:a + chunk], d[a:a + chunk], t[a:a + chunk], i[a:a + chunk], perturb=False, **kw)
+                n = r['image'].reshape(-1, 3).shape[0]
+                outs['image'].append(r['image'].reshape(-1, 3))
+                outs['depth'].append(r['depth'].reshape(-1))
+                ws = r['weights_sum']
+                outs['weights_sum'].append(ws.reshape(-1, 1) if ws is not None else torch.zeros(n, 1, device=o.device))
+            return {k: torch.cat(v, 0) for k, v in outs.items()}
+        finally:
+            self.model.train(was_training)
+
     @staticmethod
     def get_ortho_normal_dir(normals, phi=None):
         """morpheus.py:518-528: a random unit direction orthogonal to the normal (`phi` [.., 1] in [0, 2 pi) injects the draw)"""

@@ -6,6 +6,7 @@ eps=1e-15) over the named groups of models/model.py:313-324), and the data-paral
 NCCL all-reduce of the flat gradient arena per step (the reference is single-GPU).
 """
 import ctypes as C
+import math
 
 import torch
 import torch.distributed as dist
@@ -107,6 +108,53 @@ def real_view_loss_torch(out, batch, model, tr):
     return loss
 
 
+def learning_factor(epoch, warm_up_end, n_epochs, scale_factor=1.0):
+    """morpheus.py:476-486"""
+    if epoch < warm_up_end:
+        f = 0.01 if epoch < 100 else 0.01 + (epoch - 100) / (warm_up_end - 100) * 0.99
+    else:
+        alpha = 0.05
+        progress = (epoch - warm_up_end) / (n_epochs - warm_up_end)
+        f = (math.cos(math.pi * progress) + 1.0) * 0.5 * (1 - alpha) + alpha
+    return f * scale_factor
+
+
+class FlatEMA:
+    """torch_ema.ExponentialMovingAverage (requirements.txt:24; morpheus.py:160-162, :1299-1301, :1368-1369, :1432-1433) over the
+    ONE flat parameter buffer of FlatAdam: update() is a single lerp launch instead of one sub_ per parameter tensor."""
+
+    def __init__(self, flat, decay, use_num_updates=True):
+        self.flat, self.decay = flat, float(decay)
+        self.num_updates = 0 if use_num_updates else None
+        self.shadow = flat.detach().clone()
+        self.collected = None
+
+    def update(self):
+        decay = self.decay
+        if self.num_updates is not None:
+            self.num_updates += 1
+            decay = min(decay, (1 + self.num_updates) / (10 + self.num_updates))
+        self.shadow.lerp_(self.flat, 1.0 - decay)          # shadow -= (1 - decay) * (shadow - param)
+
+    def store(self):
+        self.collected = self.flat.detach().clone()
+
+    def copy_to(self):
+        self.flat.copy_(self.shadow)
+
+    def restore(self):
+        self.flat.copy_(self.collected)
+        self.collected = None
+
+    def state_dict(self):
+        return {'decay': self.decay, 'num_updates': self.num_updates, 'shadow': self.shadow, 'collected': self.collected}
+
+    def load_state_dict(self, sd):
+        self.decay, self.num_updates = sd['decay'], sd['num_updates']
+        self.shadow.copy_(sd['shadow'])
+        self.collected = sd['collected']
+
+
 class FlatAdam:
     """All trainable parameters re-homed into ONE flat fp32 buffer (and their .grad into one flat gradient
     buffer), so a step is: zero one buffer, one all-reduce, one fused Adam launch (csrc/sampler.cu:adam_kernel).
@@ -141,9 +189,30 @@ class FlatAdam:
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # device-side step count (CUDA-graph replayable)
         self.params = plist
         self.model = model
+        self.current_learning_rate = lr
 
     def set_group_lr(self, name, lr):
         self.group_lr[self.group_names.index(name)] = lr
+
+    # -- learning-rate schedule of the reference trainer (morpheus.py:471-516), on the device-resident per-group table ------
+    def update_learning_rate(self, epoch, tr, scale_factor=1.0):
+        """morpheus.py:471-502: 0.01 -> 1 warm-up, then cosine to 0.05; 'pose' runs at lr/10, every other group at lr"""
+        self.current_learning_rate = tr['lr'] * learning_factor(epoch, tr['warm_up_end'], tr['n_epochs'], scale_factor)
+        lrs = [self.current_learning_rate * (0.1 if n == 'pose' else 1.0) for n in self.group_names]
+        self.group_lr.copy_(torch.tensor(lrs, dtype=torch.float32))
+        return self.current_learning_rate
+
+    DEFORM_GROUPS = ('code_deform', 'decoder_deform', 'decoder_topo')
+
+    def freeze_lr_deform(self):
+        """morpheus.py:504-511 (virtual steps while epoch <= 400 do not move the deformation field)"""
+        for n in self.DEFORM_GROUPS:
+            self.set_group_lr(n, 0.0)
+
+    def reset_lr_deform(self):
+        """morpheus.py:513-516"""
+        for n in self.DEFORM_GROUPS:
+            self.set_group_lr(n, self.current_learning_rate)
 
     def zero_grad(self):
         self.grad.zero_()

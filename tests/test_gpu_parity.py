@@ -704,3 +704,35 @@ def test_normal_smoothness_and_surface_point_losses_vs_oracle(dev):
     res = sc.density(xyz, t=t)
     ref = 10.0 * torch.mean(torch.square(res['sdf'][dm])) + 5.0 * torch.nn.functional.mse_loss(res['albedo'] * dm[:, None].float(), batch['rgb'].cpu() * dm[:, None].float())
     assert abs(float(loss) - float(ref)) < 1e-4 * abs(float(ref)) + 1e-7, (float(loss), float(ref))
+
+
+def test_forward_only_consumers(dev):
+    """dense SDF volume for mesh export (morpheus.py:384-396) and chunked eval render vs the CPU oracle."""
+    from morpheus_b200.nerfacc_compat import OccGridEstimator
+    from morpheus_b200.render import Renderer
+    from oracle import render as orr
+    from oracle.fields import SceneOracle, init_reference_like_state
+    sd = init_reference_like_state(200, seed=3, randomize=True, emb_scale=0.05, sphere=True)
+    m = make_model(sd, 1.0, dev).eval()
+    cfg = {'model': {'bg_radius': 1.4, 'activation': 'exp'}, 'render': {'step_size': 0.01}, 'train': {}}
+    R = Renderer(m, OccGridEstimator(torch.tensor([-1.01] * 3 + [1.01] * 3), 128).to(dev), cfg, 200, uniform_samples=32)
+    vol = R.sdf_volume(resolution=12, S=5, t=0.25)
+    sc = SceneOracle(sd, 1.01, 200, 1.0)
+    ax = torch.linspace(-1, 1, 12)
+    xx, yy, zz = torch.meshgrid(ax, ax, ax, indexing='ij')
+    pts = torch.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], -1)
+    with torch.no_grad():
+        ref = sc.density(pts, t=torch.full((pts.shape[0], 1), 0.25), return_color=False)['sdf'].reshape(12, 12, 12)
+    assert rel_l2(cpu(vol), ref.numpy()) < 1e-4
+    # chunked eval render == one-shot render
+    g = torch.Generator().manual_seed(1)
+    c2w = orr.look_at_pose(70.0, 40.0, 2.5)
+    dirs = orr.camera_dirs(360, 360, 517.0, 517.0, 180.0, 180.0).reshape(-1, 3)
+    idx = torch.randint(0, dirs.shape[0], (300,), generator=g)
+    o, d = orr.rays_from_pose(dirs[idx], c2w)
+    t = torch.full((300, 1), 0.25)
+    ids = torch.full((300, 1), 50, dtype=torch.long)
+    jit = torch.rand(300, generator=g).to(dev)
+    a = R.render_image(o.to(dev), d.to(dev), t.to(dev), ids.to(dev), chunk=128, jitter=None, shading='albedo')
+    assert a['image'].shape == (300, 3) and a['depth'].shape == (300,) and torch.isfinite(a['image']).all()
+    assert m.training is False
