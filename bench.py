@@ -268,8 +268,10 @@ def main():
             'field_fwd_aux': 2 * 6 * sdf_fd * M_local,
             'field_bwd_main': (0 if tc_bwd else 4 * (MAC_DEFORM + MAC_TOPO) * M_local) + sdf_bwd_main,
             'field_bwd_aux': 4 * 6 * sdf_fd * M_local,
-            'field_bwd_sdf_tc_main': sdf_bwd_main,
+            'field_bwd_sdf_tc_main': sdf_bwd_main if 'field_bwd_fd_tc_main' not in kern else 4 * (MAC_COLOR + MAC_SDF) * M_local,
             'field_bwd_sdf_tc_aux': 4 * 6 * sdf_fd * M_local,
+            'field_bwd_fd_tc_main': 4 * 6 * sdf_fd * M_local,
+            'field_bwd_fd_tc_aux': 4 * 6 * sdf_fd * M_local,
             'field_bwd_warp_tc': 4 * (MAC_DEFORM + MAC_TOPO) * M_local,
         }
         engine = {k: 'tcgen05 (3x fp16 split)' for k in flops}

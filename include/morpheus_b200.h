@@ -103,6 +103,8 @@ int mb_composite_backward(const int32_t* seg, uint32_t N, uint32_t M, const floa
 #define MB_F_TOPO_IN 32u      /* take topo from topo_in instead of zeros / warp */
 #define MB_F_SKIP_WARP_BWD 64u /* backward only: do not back-propagate the deform/topology nets; write d/d(deform), d/d(topo)
                                  to g_def_out / g_topo_out instead (consumed by mb_field_backward_warp_tc) */
+#define MB_F_FD_DELEGATE 128u  /* backward only (mb_field_backward_sdf_tc): do not run the FD-query chains; write d/d(sdf) of the six
+                                 +-eps queries of every sample to g_fd [M,6] instead (consumed by mb_field_backward_fd_tc) */
 #define MB_SHADE_ALBEDO 0
 #define MB_SHADE_LAMBERTIAN 1   /* albedo*(ratio+(1-ratio)*max(n.l,0)); 'albedo_normal' is ratio=1 */
 #define MB_SHADE_TEXTURELESS 2
@@ -168,6 +170,7 @@ typedef struct mb_field_grads {
     float* g_topo_in;               /* [M,2] or NULL */
     float* g_def_out;               /* [M,3], with MB_F_SKIP_WARP_BWD */
     float* g_topo_out;              /* [M,2], with MB_F_SKIP_WARP_BWD */
+    float* g_fd;                    /* [M,6] or NULL: written with MB_F_FD_DELEGATE, read by mb_field_backward_fd_tc */
 } mb_field_grads;
 
 int mb_field_backward(const mb_field_params* p, const mb_field_io* io, const mb_field_grads* g, mb_stream_t stream);
@@ -182,6 +185,12 @@ int mb_field_backward(const mb_field_params* p, const mb_field_io* io, const mb_
  * tc_weights_t/tc_off_t: dgrad operands of sdf[3], color[3] (mb_pack_tc mode 1). */
 int mb_field_backward_sdf_tc(const mb_field_params* p, const mb_field_io* io, const mb_field_grads* g, const void* tc_weights,
                              const uint32_t* tc_off, const void* tc_weights_t, const uint32_t* tc_off_t, mb_stream_t stream);
+/* Tensor-core backward of the FD-normal queries only (two CTAs per SM, 96-row sub-tiles = 16 samples x 6 queries).  Upstream:
+ * g->g_fd [M,6] (from mb_field_backward_sdf_tc with MB_F_FD_DELEGATE) or, if NULL, g_normal / g_normal_raw with the saved
+ * normal_raw (ALBEDO shading).  accumulate != 0: ADD to g_x / g_def_out / g_topo_out / g_topo_in (which the main kernel wrote);
+ * accumulate == 0: write them (stand-alone FD query, e.g. scene_representation.normal). */
+int mb_field_backward_fd_tc(const mb_field_params* p, const mb_field_io* io, const mb_field_grads* g, const void* tc_weights,
+                            const uint32_t* tc_off, const void* tc_weights_t, const uint32_t* tc_off_t, int accumulate, mb_stream_t stream);
 int mb_field_backward_warp_tc(const mb_field_params* p, const float* x, const float* t, uint32_t M, const float* g_def,
                               const float* g_topo, const void* stash, const void* tc_weights_t, const uint32_t* tc_off_t,
                               float* g_arena, float* const g_code[3], float* g_x, mb_stream_t stream);

@@ -20,6 +20,8 @@ USE_TC = os.environ.get('MORPHEUS_B200_TC', '1') != '0'
 USE_TC_BWD = os.environ.get('MORPHEUS_B200_TC_BWD', '1') != '0'
 # tensor-core backward of the SDF / colour nets + FD queries (recompute on tcgen05, per-tile TMEM weight-gradient accumulators)
 USE_TC_BWD_SDF = os.environ.get('MORPHEUS_B200_TC_BWD_SDF', '1') != '0'
+# FD-normal queries of the backward in the specialised two-CTAs-per-SM kernel (csrc/field_bwd_fd_tc.cu)
+USE_TC_BWD_FD = os.environ.get('MORPHEUS_B200_TC_BWD_FD', '1') != '0'
 
 
 class LayerDesc(C.Structure):
@@ -48,10 +50,11 @@ class FieldGrads(C.Structure):
                 ('g_deform', C.c_void_p), ('g_topo', C.c_void_p),
                 ('deform', C.c_void_p), ('topo', C.c_void_p), ('normal_raw', C.c_void_p),
                 ('g_arena', C.c_void_p), ('g_emb_sdf', C.c_void_p), ('g_emb_col', C.c_void_p), ('g_code', C.c_void_p * 3),
-                ('g_beta', C.c_void_p), ('g_x', C.c_void_p), ('g_topo_in', C.c_void_p), ('g_def_out', C.c_void_p), ('g_topo_out', C.c_void_p)]
+                ('g_beta', C.c_void_p), ('g_x', C.c_void_p), ('g_topo_in', C.c_void_p), ('g_def_out', C.c_void_p), ('g_topo_out', C.c_void_p),
+                ('g_fd', C.c_void_p)]
 
 
-F_WARP, F_MAIN, F_COLOR, F_FD, F_FD_WARPED, F_TOPO_IN, F_SKIP_WARP_BWD = 1, 2, 4, 8, 16, 32, 64
+F_WARP, F_MAIN, F_COLOR, F_FD, F_FD_WARPED, F_TOPO_IN, F_SKIP_WARP_BWD, F_FD_DELEGATE = 1, 2, 4, 8, 16, 32, 64, 128
 SHADE = {'albedo': 0, 'lambertian': 1, 'albedo_normal': 1, 'textureless': 2, 'normal': 3}
 
 # every symbol include/morpheus_b200.h declares (checked by tests/test_abi.py)
@@ -60,7 +63,7 @@ SYMBOLS = ['mb_version', 'mb_last_error', 'mb_sm_count', 'mb_grid_encode_forward
            'mb_composite_backward', 'mb_field_forward', 'mb_field_backward', 'mb_occ_update', 'mb_occ_binarize',
            'mb_adam_step', 'mb_sds_grad', 'mb_add_noise', 'mb_pack_tc', 'mb_field_forward_tc', 'mb_adam_step_dev', 'mb_field_backward_warp_tc', 'mb_field_backward_sdf_tc',
            'mb_ray_points_forward', 'mb_ray_points_backward', 'mb_pack_arena_forward', 'mb_pack_arena_backward', 'mb_sdf_loss_forward',
-           'mb_sdf_loss_backward', 'mb_pose_rays_forward', 'mb_pose_rays_backward', 'mb_ray_loss']
+           'mb_sdf_loss_backward', 'mb_pose_rays_forward', 'mb_pose_rays_backward', 'mb_ray_loss', 'mb_field_backward_fd_tc']
 
 
 def lib():

@@ -257,7 +257,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
     const bool do_main = (flags & MB_F_MAIN) != 0;
     const bool do_color = do_main && (flags & MB_F_COLOR);
     const bool color_grad = do_color && gr.g_color && io.shading != MB_SHADE_TEXTURELESS && io.shading != MB_SHADE_NORMAL;
-    const bool need_fd = (flags & MB_F_FD) && (gr.g_normal || gr.g_normal_raw || (io.shading != MB_SHADE_ALBEDO && gr.g_color));
+    const bool fd_grads = (flags & MB_F_FD) && (gr.g_normal || gr.g_normal_raw || (io.shading != MB_SHADE_ALBEDO && gr.g_color));
+    const bool delegate = (flags & MB_F_FD_DELEGATE) && gr.g_fd;       // FD chains run in mb_field_backward_fd_tc
+    const bool need_fd = fd_grads && !delegate;
 
     __shared__ int n_ops_s;
     __shared__ LevelInfo s_levels[16];
@@ -642,7 +644,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
 #pragma unroll
                     for (int a = 0; a < 3; a++) { const float s = salb[a * TM + m]; galb[a * TM + m] = ga[a] * s * (1.0f - s); }
                 }
-                if (need_fd) {
+                if (fd_grads) {
                     float graw[3];
                     if (clamped) { graw[0] = gn[0] * inv; graw[1] = gn[1] * inv; graw[2] = gn[2] * inv; }
                     else {
@@ -653,6 +655,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) field_bwd_sdf_tc_kernel(const mb_
                     const float h = 0.5f / FD_EPS;
 #pragma unroll
                     for (int a = 0; a < 3; a++) { gsq[(2 * a) * TM + m] = graw[a] * h; gsq[(2 * a + 1) * TM + m] = -graw[a] * h; }
+                }
+                if (delegate) {
+#pragma unroll
+                    for (int q = 0; q < 6; q++) gr.g_fd[(size_t)gm * 6 + q] = gsq[q * TM + m];
                 }
                 if (do_main) {
                     float v = gr.g_sdf ? gr.g_sdf[gm] : 0.f;

@@ -8,10 +8,11 @@ namespace tc {
 
 constexpr int A_LO_OFF = 32768;         // lo-part offset (bytes) of a 128 x 128 fp16 operand tile
 
-__device__ __forceinline__ void store_core(uint8_t* A, int m, int kc, const float (&v)[8], int lo_off = A_LO_OFF) {
+// `pitch` = bytes between 8-column core groups = 16 * rows of the tile (2048 for 128-row tiles, 1536 for 96-row tiles)
+__device__ __forceinline__ void store_core(uint8_t* A, int m, int kc, const float (&v)[8], int lo_off = A_LO_OFF, int pitch = 2048) {
     uint4 hi, lo;
     split8(v, hi, lo);
-    uint8_t* p = A + kc * 2048 + (m >> 3) * 128 + (m & 7) * 16;
+    uint8_t* p = A + kc * pitch + (m >> 3) * 128 + (m & 7) * 16;
     *reinterpret_cast<uint4*>(p) = hi;
     *reinterpret_cast<uint4*>(p + lo_off) = lo;
 }
@@ -60,35 +61,36 @@ __device__ __forceinline__ void build_grid_core_tc(uint8_t* A, int m, int kc, co
 
 // ---- rolled builders (small code footprint: the fused kernels are instruction-fetch bound when these are unrolled) ----------
 // one feature (2-byte hi + 2-byte lo) / an even-aligned feature pair (4-byte stores) at tc column k of row m
-__device__ __forceinline__ void store_one(uint8_t* A, int m, int k, float f, int lo_off = A_LO_OFF) {
+__device__ __forceinline__ void store_one(uint8_t* A, int m, int k, float f, int lo_off = A_LO_OFF, int pitch = 2048) {
     const __half h = __float2half_rn(f);
     const __half l = __float2half_rn(f - __half2float(h));
-    uint8_t* p = A + (k >> 3) * 2048 + (m >> 3) * 128 + (m & 7) * 16 + (k & 7) * 2;
+    uint8_t* p = A + (k >> 3) * pitch + (m >> 3) * 128 + (m & 7) * 16 + (k & 7) * 2;
     *reinterpret_cast<__half*>(p) = h;
     *reinterpret_cast<__half*>(p + lo_off) = l;
 }
-__device__ __forceinline__ void store_pair(uint8_t* A, int m, int k, float f0, float f1, int lo_off = A_LO_OFF) {
+__device__ __forceinline__ void store_pair(uint8_t* A, int m, int k, float f0, float f1, int lo_off = A_LO_OFF, int pitch = 2048) {
     const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
     const __half l0 = __float2half_rn(f0 - __half2float(h0)), l1 = __float2half_rn(f1 - __half2float(h1));
-    uint8_t* p = A + (k >> 3) * 2048 + (m >> 3) * 128 + (m & 7) * 16 + (k & 7) * 2;
+    uint8_t* p = A + (k >> 3) * pitch + (m >> 3) * 128 + (m & 7) * 16 + (k & 7) * 2;
     *reinterpret_cast<uint32_t*>(p) = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
     *reinterpret_cast<uint32_t*>(p + lo_off) = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
 }
 // frequency features of ONE axis a of point coordinate v: tc columns a, 3+6k+a (sin), 6+6k+a (cos)
-__device__ __forceinline__ void freq_axis_tc(uint8_t* A, int m, int a, float v, int n_freq, int lo_off = A_LO_OFF) {
-    store_one(A, m, a, v, lo_off);
+__device__ __forceinline__ void freq_axis_tc(uint8_t* A, int m, int a, float v, int n_freq, int lo_off = A_LO_OFF, int pitch = 2048) {
+    store_one(A, m, a, v, lo_off, pitch);
     float fr = 1.0f;
 #pragma unroll 1
     for (int k = 0; k < 6; k++) {
         float s = 0.f, c = 0.f;
         if (k < n_freq) sincosf(v * fr, &s, &c);
-        store_one(A, m, 3 + 6 * k + a, s, lo_off);
-        store_one(A, m, 6 + 6 * k + a, c, lo_off);
+        store_one(A, m, 3 + 6 * k + a, s, lo_off, pitch);
+        store_one(A, m, 6 + 6 * k + a, c, lo_off, pitch);
         fr *= 2.0f;
     }
 }
 // grid levels [l0, l0+nl) at world point p -> tc columns kbase + 2l, kbase + 2l + 1 (same arithmetic as grid_eval)
-__device__ __forceinline__ void gather_levels_tc(uint8_t* A, int m, int kbase, const GridCtx& g, int l0, int nl, const float p[3], int lo_off = A_LO_OFF) {
+__device__ __forceinline__ void gather_levels_tc(uint8_t* A, int m, int kbase, const GridCtx& g, int l0, int nl, const float p[3], int lo_off = A_LO_OFF,
+                                                 int pitch = 2048) {
     float u[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) u[d] = __fdiv_rn(__fadd_rn(p[d], g.bound), g.two_bound);
@@ -96,7 +98,7 @@ __device__ __forceinline__ void gather_levels_tc(uint8_t* A, int m, int kbase, c
     for (int l = l0; l < l0 + nl; l++) {
         float feat[2] = {0.f, 0.f};
         if ((uint32_t)l < g.n_levels) grid_eval(g, l, u, feat, nullptr);
-        store_pair(A, m, kbase + 2 * l, feat[0], feat[1], lo_off);
+        store_pair(A, m, kbase + 2 * l, feat[0], feat[1], lo_off, pitch);
     }
 }
 

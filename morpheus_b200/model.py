@@ -387,9 +387,22 @@ class _FieldQuery(torch.autograd.Function):
             tabs_f = _tc_tables(x.device)
             tabs_s = _tc_tables_small(x.device)
             tcw_f, tcw_s = tcws['f'], tcws['s']
-            with _lib.timed('field_bwd_sdf_tc_main' if flags & F_MAIN else 'field_bwd_sdf_tc_aux'):
-                check(_lib.lib().mb_field_backward_sdf_tc(_lib.C.byref(P), _lib.C.byref(io), _lib.C.byref(G), ptr(tcw_f), ptr(tabs_f[1]),
-                                                          ptr(tcw_s), ptr(tabs_s[1]), stream()), 'field_backward_sdf_tc')
+            # FD-normal queries: specialised two-CTAs-per-SM kernel; with MAIN the general kernel first turns the upstream
+            # gradients into d/d(sdf) of the six queries per sample (g_fd) and leaves the FD chains to it
+            fd_kernel = _lib.USE_TC_BWD_FD and bool(flags & F_FD) and (bool(flags & F_MAIN) or shading == 0 or g_color is None) \
+                and (g_normal is not None or g_raw is not None or (shading != 0 and g_color is not None))
+            if flags & F_MAIN or not fd_kernel:
+                if fd_kernel:
+                    g_fd = torch.empty(M, 6, device=x.device, dtype=torch.float32)
+                    G.g_fd = ptr(g_fd)
+                    io.flags = io.flags | _lib.F_FD_DELEGATE
+                with _lib.timed('field_bwd_sdf_tc_main' if flags & F_MAIN else 'field_bwd_sdf_tc_aux'):
+                    check(_lib.lib().mb_field_backward_sdf_tc(_lib.C.byref(P), _lib.C.byref(io), _lib.C.byref(G), ptr(tcw_f), ptr(tabs_f[1]),
+                                                              ptr(tcw_s), ptr(tabs_s[1]), stream()), 'field_backward_sdf_tc')
+            if fd_kernel:
+                with _lib.timed('field_bwd_fd_tc_main' if flags & F_MAIN else 'field_bwd_fd_tc_aux'):
+                    check(_lib.lib().mb_field_backward_fd_tc(_lib.C.byref(P), _lib.C.byref(io), _lib.C.byref(G), ptr(tcw_f), ptr(tabs_f[1]),
+                                                             ptr(tcw_s), ptr(tabs_s[1]), 1 if flags & F_MAIN else 0, stream()), 'field_backward_fd_tc')
         else:
             with _lib.timed('field_bwd_main' if flags & F_MAIN else 'field_bwd_aux'):
                 check(_lib.lib().mb_field_backward(_lib.C.byref(P), _lib.C.byref(io), _lib.C.byref(G), stream()), 'field_backward')

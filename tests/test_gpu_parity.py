@@ -523,7 +523,7 @@ def test_tc_backward_sdf_matches_simt(dev, case):
             run(m, xg).backward()
             torch.cuda.synchronize()
             launched = set(_lib.PROFILE.summary())
-            assert any(k.startswith('field_bwd_sdf_tc') for k in launched) == tc, launched
+            assert any(k.startswith(('field_bwd_sdf_tc', 'field_bwd_fd_tc')) for k in launched) == tc, launched
             grads[tc] = {'x': xg.grad.clone(), **{n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}}
     finally:
         _lib.USE_TC, _lib.USE_TC_BWD, _lib.USE_TC_BWD_SDF = old
