@@ -191,6 +191,8 @@ int mb_field_backward_sdf_tc(const mb_field_params* p, const mb_field_io* io, co
  * accumulate == 0: write them (stand-alone FD query, e.g. scene_representation.normal). */
 int mb_field_backward_fd_tc(const mb_field_params* p, const mb_field_io* io, const mb_field_grads* g, const void* tc_weights,
                             const uint32_t* tc_off, const void* tc_weights_t, const uint32_t* tc_off_t, int accumulate, mb_stream_t stream);
+/* debug: cumulative clock64 cycles per phase of mb_field_backward_fd_tc, summed over CTAs (16 host words); reset != 0 clears */
+int mb_debug_fd_phases(unsigned long long* host_out16, int reset);
 int mb_field_backward_warp_tc(const mb_field_params* p, const float* x, const float* t, uint32_t M, const float* g_def,
                               const float* g_topo, const void* stash, const void* tc_weights_t, const uint32_t* tc_off_t,
                               float* g_arena, float* const g_code[3], float* g_x, mb_stream_t stream);

@@ -9,6 +9,8 @@
 //     dW2[0,:] += g0 * A2 (column sums by warp shuffles); A2 itself is never stored;
 //   * per sub-tile: S0 -> [MMA] -> A1 -> [MMA] -> dZ1 -> [MMA: wgrad1, dgrad1] -> dZ0 -> [MMA: wgrad0, dgrad0] -> d(S0)
 //     -> sin/cos backward + hash-grid backward (per-cell merged red.v2 scatter, corner-difference d/dx);
+//   * bias gradients ride on the weight-gradient MMAs: pad column 39 of S0 and an extra column 64 of A1 hold the constant 1, so
+//     row 39 / row 64 of the dW accumulators are the column sums of dZ0 / dZ1 (no shuffle reductions);
 //   * weight-gradient accumulators (sdf0: 80 x 64, sdf1: 64 x 64) live in TMEM for a whole 128-sample tile (8 sub-tiles)
 //     and are flushed once per tile; 256 TMEM columns per CTA.
 // Gradients are scaled per tile by a power of two before the fp16 (hi, lo) split; 3 MMAs per product (tc_common.cuh).
@@ -26,16 +28,18 @@ constexpr int RT = 96;                  // rows per sub-tile
 constexpr int NSUB = TM * 6 / RT;       // 8
 constexpr int NWORK = 256;
 constexpr int NTHREADS = NWORK + 64;    // + MMA-issue warp + weight-loader warp
-constexpr int NSTAGE = 2;
+constexpr int NSTAGE = 3;
 constexpr int STAGE_BYTES = 5120;
 constexpr int PITCH = RT * 16;          // bytes between 8-column core groups of a 96-row operand tile
 constexpr int S0_LO = 10 * PITCH;       // lo offset of the 80-column S0 tile
-constexpr int X_LO = 8 * PITCH;         // lo offset of a 64-column tile
+constexpr int X_LO = 8 * PITCH;         // lo offset of a 64-column tile (dZ)
+constexpr int X0_LO = 9 * PITCH;        // lo offset of the A1 tile: 64 columns + one core whose first column is the constant 1
+constexpr bool PHASE_TIMING = false;    // true: worker thread 0 accumulates clock64 deltas per phase (mb_debug_fd_phases; ~10 % slower)
 
 struct Smem {
     static constexpr int S0 = 0;                          // 30720
-    static constexpr int X0 = S0 + 2 * S0_LO;             // 24576
-    static constexpr int DZ = X0 + 2 * X_LO;              // 24576; G (fp32 [32][96]) aliases it after the last MMA of a sub-tile
+    static constexpr int X0 = S0 + 2 * S0_LO;             // 27648
+    static constexpr int DZ = X0 + 2 * X0_LO;             // 24576; G (fp32 [32][96]) aliases it after the last MMA of a sub-tile
     static constexpr int W = DZ + 2 * X_LO;               // NSTAGE x 5120
     static constexpr int F = W + NSTAGE * STAGE_BYTES;
     static constexpr int SP = F;                          // [3][128] sample points (x or x + deform)
@@ -55,6 +59,9 @@ struct Smem {
 };
 static_assert(Smem::BAR % 8 == 0, "alignment");
 static_assert(Smem::TOTAL <= 113 * 1024, "two CTAs per SM");
+
+// phase timing (clock64 deltas of worker thread 0 of every CTA, summed): read back with mb_debug_fd_phases()
+__device__ unsigned long long g_fd_phase[16];
 
 __device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -274,8 +281,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
             for (uint32_t it = 0; it < my_tiles; it++) {
                 for (int j = 0; j < NSUB; j++) {
                     wait_z(); gemm_ring(s0_base, S0_LO, 5, 64, 64); umma_commit(acc_ready);                                   // A1 = S0 W0^T
-                    wait_z(); gemm_ring(x0_base, X_LO, 4, 64, 64); umma_commit(acc_ready);                                    // A2 = A1 W1^T
-                    wait_z(); wgrad(x0_base, X_LO, 192, j == 0); gemm_ring(dz_base, X_LO, 4, 64, 64); umma_commit(acc_ready);  // dW1, dA1
+                    wait_z(); gemm_ring(x0_base, X0_LO, 4, 64, 64); umma_commit(acc_ready);                                    // A2 = A1 W1^T
+                    wait_z(); wgrad(x0_base, X0_LO, 192, j == 0); gemm_ring(dz_base, X_LO, 4, 64, 64); umma_commit(acc_ready);  // dW1, dA1
                     wait_z(); wgrad(s0_base, S0_LO, 128, j == 0); gemm_ring(dz_base, X_LO, 4, 80, 80); umma_commit(acc_ready); // dW0, dS0
                 }
             }
@@ -295,7 +302,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
         auto bar_workers = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory"); };
         auto signal_z = [&]() { fence_proxy_async(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(z_ready); };
         auto wait_acc = [&]() { mbar_wait(acc_ready, acc_count & 1); acc_count++; tc_fence_after(); };
+        unsigned long long ph[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        long long tprev = clock64();
+#define FD_PHASE(i) do { if (PHASE_TIMING && tid == 0) { const long long tn = clock64(); ph[i] += (unsigned long long)(tn - tprev); tprev = tn; } } while (0)
 
+        if (tid < RT) {      // core 8 of the A1 tile: column 64 = 1 (never overwritten: the A1 epilogue writes cores 0..7 only)
+            const float one8[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            store_core(X0, tid, 8, one8, X0_LO, PITCH);
+        }
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const uint32_t m0 = tile * TM;
             const int nv = (int)min((uint32_t)TM, io.M - m0);
@@ -373,6 +387,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
             }
             bar_workers();
             const float scale = misc[4], inv_scale = misc[5];
+            FD_PHASE(0);      // tile prologue
 
 #pragma unroll 1
             for (int j = 0; j < NSUB; j++) {
@@ -392,6 +407,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
                     stq[RT + tid] = stopo[TM + s];
                 }
                 bar_workers();
+                FD_PHASE(1);      // row setup + barrier
                 // ---- S0: 16 levels x 96 rows in pairs of levels (768 items) + 3 axes x 96 rows of frequency features + pads ----
                 for (int it = tid; it < 8 * RT; it += NWORK) {
                     const int r = it % RT, lp = it / RT;
@@ -403,13 +419,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
                     if (a < 3) {
                         freq_axis_tc(S0, r, a, spt[a * RT + r], (int)p.n_freq, S0_LO, PITCH);
                     } else {
-                        store_one(S0, r, 39, 0.f, S0_LO, PITCH);
+                        store_one(S0, r, 39, 1.0f, S0_LO, PITCH);      // constant-1 pad feature (its W0 column is zero): db0 from the wgrad MMA
                         const float v[8] = {stq[r], stq[RT + r], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                         store_core(S0, r, 9, v, S0_LO, PITCH);
                     }
                 }
+                FD_PHASE(2);      // gather + encodings
                 // ---- A1 = relu(S0 W0^T + b0) -> X0 ----
                 signal_z(); wait_acc();
+                FD_PHASE(3);      // wait MMA fwd0
                 if (erow) {
                     float v[32];
                     tmem_ld32(tmem + lane_base + h * 32, v);
@@ -419,11 +437,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
                         float o[8];
 #pragma unroll
                         for (int i = 0; i < 8; i++) o[i] = fmaxf(v[c * 8 + i] + __ldg(b0 + c * 8 + i), 0.f);
-                        store_core(X0, m, h * 4 + c, o, X_LO, PITCH);
+                        store_core(X0, m, h * 4 + c, o, X0_LO, PITCH);
                     }
                 }
+                FD_PHASE(4);      // epilogue A1
                 // ---- A2 = relu(A1 W1^T + b1): dZ1 = g0 W2[0,:] (A2 > 0) -> DZ ; dW2[0,:] += g0 A2 ; db1 += dZ1 ----
                 signal_z(); wait_acc();
+                FD_PHASE(5);      // wait MMA fwd1
                 {
                     float z[32], ga[32];
                     if (erow) {
@@ -451,14 +471,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
                         for (int i = 0; i < 32; i++) z[i] = ga[i] = 0.f;
                     }
                     if (q4 < 3) {       // warp-uniform
-                        const float cz = warp_colsum32(z, lane);
-                        atomicAdd(csb + h * 32 + lane, cz);
                         const float cg = warp_colsum32(ga, lane);
                         atomicAdd(cw2 + h * 32 + lane, cg);
                     }
                 }
+                FD_PHASE(6);      // fused epilogue A2 -> dZ1
                 // ---- dZ0 = (dZ1 W1) (A1 > 0) -> DZ ; db0 += dZ0 ----
                 signal_z(); wait_acc();
+                FD_PHASE(7);      // wait MMA bwd1
                 if (q4 < 3) {
                     float v[32];
                     tmem_ld32(tmem + lane_base + h * 32, v);
@@ -473,15 +493,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
                             const uint16_t hb = (uint16_t)(aw[i >> 1] >> ((i & 1) * 16));
                             const bool pos = (hb & 0x7FFF) != 0 && !(hb & 0x8000);
                             o[i] = pos ? v[c * 8 + i] : 0.f;
-                            v[c * 8 + i] = o[i];
                         }
                         store_core(DZ, m, kc, o, X_LO, PITCH);
                     }
-                    const float cz = warp_colsum32(v, lane);
-                    atomicAdd(csb + 64 + h * 32 + lane, cz);
                 }
+                FD_PHASE(8);      // epilogue dZ0
                 // ---- d(S0) (80 columns): h = 0: frequency columns 0..38 -> sin/cos backward ; h = 1: grid columns 40..71 -> G, topo 72..73 ----
                 signal_z(); wait_acc();
+                FD_PHASE(9);      // wait MMA bwd0
                 if (erow) {
                     if (h == 0) {
                         float v[32], w[8];
@@ -522,8 +541,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
                 }
                 tc_fence_before();
                 bar_workers();
+                FD_PHASE(10);     // epilogue d(S0) + barrier
                 grid_bwd_samples(gs, spt, G, gr.g_emb_sdf, gpt, inv_scale, tid);
                 bar_workers();
+                FD_PHASE(11);     // table scatter + barrier
                 // ---- fold the row gradients into the sample gradients (clamp derivative) ----
                 if (tid < RT) {
                     const int s = 16 * j + tid / 6, qq = tid % 6;
@@ -538,6 +559,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
                 }
             }
 
+            FD_PHASE(12);         // fold (last sub-tile)
             // ---- flush the weight-gradient accumulators of the tile: rows = input features (tc order), 32 columns per warp half ----
             {
                 const int krow = q4 * 32 + lane;
@@ -551,23 +573,27 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
                             float* dst = GA + p.sdf[0].wt_off + (size_t)korig * p.sdf[0].N_pad + h * 32;
 #pragma unroll
                             for (int c = 0; c < 8; c++) red_add4(dst + 4 * c, v[4 * c] * inv_scale, v[4 * c + 1] * inv_scale, v[4 * c + 2] * inv_scale, v[4 * c + 3] * inv_scale);
+                        } else if (krow == 39) {       // the constant-1 feature: column sums of dZ0 = bias gradient of layer 0
+                            float* dst = GA + p.sdf[0].b_off + h * 32;
+#pragma unroll
+                            for (int c = 0; c < 8; c++) red_add4(dst + 4 * c, v[4 * c] * inv_scale, v[4 * c + 1] * inv_scale, v[4 * c + 2] * inv_scale, v[4 * c + 3] * inv_scale);
                         }
                     }
                 }
                 {   // sdf layer 1: 64 rows x 64 columns at TMEM column 192
-                    if (q4 < 2) {
+                    if (q4 < 3) {
                         float v[32];
                         tmem_ld32(tmem + lane_base + 192 + h * 32, v);
-                        float* dst = GA + p.sdf[1].wt_off + (size_t)krow * p.sdf[1].N_pad + h * 32;
+                        float* dst = (krow < 64) ? GA + p.sdf[1].wt_off + (size_t)krow * p.sdf[1].N_pad + h * 32
+                                                 : GA + p.sdf[1].b_off + h * 32;      // row 64 = constant-1 feature: bias gradient of layer 1
+                        if (krow <= 64) {
 #pragma unroll
-                        for (int c = 0; c < 8; c++) red_add4(dst + 4 * c, v[4 * c] * inv_scale, v[4 * c + 1] * inv_scale, v[4 * c + 2] * inv_scale, v[4 * c + 3] * inv_scale);
+                            for (int c = 0; c < 8; c++) red_add4(dst + 4 * c, v[4 * c] * inv_scale, v[4 * c + 1] * inv_scale, v[4 * c + 2] * inv_scale, v[4 * c + 3] * inv_scale);
+                        }
                     }
                 }
             }
-            if (tid < 128) {
-                const float sv = csb[tid];
-                if (sv != 0.f) red_add(GA + (tid < 64 ? p.sdf[1].b_off : p.sdf[0].b_off) + (tid & 63), sv * inv_scale);
-            } else if (tid < 192) {
+            if (tid >= 128 && tid < 192) {
                 const float sv = cw2[tid - 128];       // dW2[0][k]: Wt slot [k][n = 0]
                 if (sv != 0.f) red_add(GA + p.sdf[2].wt_off + (size_t)(tid - 128) * p.sdf[2].N_pad, sv * inv_scale);
             }
@@ -598,7 +624,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
                 }
             }
             bar_workers();
+            FD_PHASE(13);         // flush + outputs
         }
+        if (PHASE_TIMING && tid == 0) {
+#pragma unroll
+            for (int i = 0; i < 14; i++) atomicAdd(&g_fd_phase[i], ph[i]);
+        }
+#undef FD_PHASE
     }
     tc_fence_before();
     __syncthreads();
@@ -637,4 +669,13 @@ extern "C" int mb_field_backward_fd_tc(const mb_field_params* p, const mb_field_
     tcf::field_bwd_fd_tc_kernel<<<grid, tcf::NTHREADS, smem, (cudaStream_t)stream>>>(*p, *io, *g, (const uint8_t*)tc_weights, tc_off,
                                                                                      (const uint8_t*)tc_weights_t, tc_off_t, accumulate);
     return check_launch("field_backward_fd_tc");
+}
+
+/* debug: cumulative clock64 cycles per phase of mb_field_backward_fd_tc (worker thread 0 of every CTA); reset != 0 clears them */
+extern "C" int mb_debug_fd_phases(unsigned long long* host_out16, int reset) {
+    using namespace mb;
+    unsigned long long z[16] = {0};
+    if (host_out16 && cudaMemcpyFromSymbol(host_out16, tcf::g_fd_phase, sizeof(z)) != cudaSuccess) { set_error("debug_fd_phases: copy failed"); return MB_ECUDA; }
+    if (reset && cudaMemcpyToSymbol(tcf::g_fd_phase, z, sizeof(z)) != cudaSuccess) { set_error("debug_fd_phases: reset failed"); return MB_ECUDA; }
+    return MB_OK;
 }

@@ -39,3 +39,14 @@ for it in range(6):
     torch.cuda.synchronize()
 for k, v in _lib.PROFILE.summary().items():
     print(f'{mode} {k}: {v["avg_ms"]:.3f} ms')
+
+if mode in ('aux', 'bwd'):
+    import ctypes as C
+    buf = (C.c_ulonglong * 16)()
+    _lib.check(_lib.lib().mb_debug_fd_phases(buf, 1), 'debug_fd_phases')
+    names = ['tile prologue', 'row setup+bar', 'gather+enc', 'wait fwd0', 'epi A1', 'wait fwd1', 'epi A2->dZ1', 'wait bwd1', 'epi dZ0', 'wait bwd0',
+             'epi dS0+bar', 'scatter+bar', 'fold(last)', 'flush+outputs']
+    tot = sum(buf[:14]) or 1
+    print('FD kernel phases (cycles of worker thread 0, all CTAs, all launches of this process):')
+    for n, v in zip(names, buf[:14]):
+        print(f'  {n:16s} {100.0 * v / tot:5.1f}%')
