@@ -165,9 +165,20 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'      # keep NCCL's own 'NCCL version ...' banner off stdout: rank 0 prints ONE JSON line
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its 'NCCL version ...' banner (and any NCCL_DEBUG output) on STDOUT when the first communicator is created:
+        # route fd 1 to stderr while that happens, so that rank 0's stdout carries exactly ONE JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     model = make_state().to(dev).train()
     state_for_cpu = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()} if rank == 0 else None
     tr = dict(mtrain.FULL_TRAIN_CFG if args.full_step else mtrain.DEFAULT_TRAIN_CFG)
