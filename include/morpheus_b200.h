@@ -228,7 +228,8 @@ int mb_ray_points_backward(const int32_t* seg, uint32_t N, const float* t_starts
 /* weight_norm + transpose + pad of the dense layers into the parameter arena (models/decoders.py:51-52 semantics).
  * layer_table: n_layers x 8 int64 {weight_v|weight ptr, weight_g ptr or 0, bias ptr, K, N, K_pad, N_pad, wt_off} (device);
  * backward writes d/d(weight_v|weight), d/d(weight_g), d/d(bias) into flat_grads at the float offsets of
- * grad_table: n_layers x 4 int64 {gv_off, gg_off, gb_off, 0}. */
+ * grad_table: n_layers x 4 int64 {gv_off, gg_off, gb_off, 0}; with flat_grads == NULL the table holds absolute device
+ * addresses (the parameters' .grad tensors) and the gradients are ACCUMULATED there. */
 int mb_pack_arena_forward(const int64_t* layer_table, int n_layers, float* arena, mb_stream_t stream);
 int mb_pack_arena_backward(const int64_t* layer_table, const int64_t* grad_table, int n_layers, const float* g_arena,
                            float* flat_grads, mb_stream_t stream);
@@ -251,6 +252,11 @@ int mb_pose_rays_backward(const float* pose, const int64_t* frame_ids, const flo
 int mb_ray_loss(const float* image, const float* opacity, const float* depth, const float* gt_rgb, const float* gt_depth,
                 const float* gt_mask, const float* rays_o, const float* rays_d, uint32_t N, float w_rgb, float w_mask, float w_depth,
                 float* out1, float* g_image, float* g_opacity, float* g_depth, mb_stream_t stream);
+
+/* deformation-code regulariser (morpheus.py:762-771): out1[0] = mean_c (2 c(t) - c(t-1/F) - c(t+1/F))^2 over the 48 channels of the three
+ * code lines code[v] [16, code_len[v]] (t_dev: device scalar).  g_out1 != NULL: backward, g_code[v] += g_out1[0] * d(out1)/d(code[v]). */
+int mb_code_reg(const float* const code[3], const int code_len[3], const float* t_dev, float inv_frames, float* out1, const float* g_out1,
+                float* const g_code[3], mb_stream_t stream);
 
 #ifdef __cplusplus
 }

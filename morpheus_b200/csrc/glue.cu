@@ -90,8 +90,10 @@ __global__ void pack_arena_fwd_kernel(const int64_t* __restrict__ tab, float* __
     if (threadIdx.x == 0) arena[b_off + n] = (n < N) ? b[n] : 0.f;
 }
 
+// direct != 0: gtab holds absolute device addresses of the parameters' .grad tensors and the gradients are ACCUMULATED there
+// (the caller's optimiser owns one flat, zero-filled gradient buffer: no per-tensor autograd accumulation launches)
 __global__ void pack_arena_bwd_kernel(const int64_t* __restrict__ tab, const int64_t* __restrict__ gtab, const float* __restrict__ g_arena,
-                                      float* __restrict__ flat) {
+                                      float* __restrict__ flat, const int direct) {
     const int64_t* t = tab + (size_t)blockIdx.y * 8;
     const int64_t* gt = gtab + (size_t)blockIdx.y * 4;
     const float* v = reinterpret_cast<const float*>(t[0]);
@@ -100,7 +102,9 @@ __global__ void pack_arena_bwd_kernel(const int64_t* __restrict__ tab, const int
     const size_t wt_off = (size_t)t[7], b_off = wt_off + 2 * (size_t)t[5] * Np;
     const int n = blockIdx.x;
     if (n >= N) return;
-    float* gv = flat + gt[0];
+    float* gv = direct ? reinterpret_cast<float*>(gt[0]) : flat + gt[0];
+    float* gg = direct ? reinterpret_cast<float*>(gt[1]) : flat + gt[1];
+    float* gb = direct ? reinterpret_cast<float*>(gt[2]) : flat + gt[2];
     __shared__ float s_dot, s_norm;
     if (g) {
         if (threadIdx.x < 32) {
@@ -117,13 +121,18 @@ __global__ void pack_arena_bwd_kernel(const int64_t* __restrict__ tab, const int
         __syncthreads();
         const float norm = s_norm, dot = s_dot, gn = g[n];
         const float s = gn / norm, c = gn * dot / (norm * norm * norm);
-        for (int k = threadIdx.x; k < K; k += blockDim.x)
-            gv[(size_t)n * K + k] = g_arena[wt_off + (size_t)k * Np + n] * s - c * v[(size_t)n * K + k];
-        if (threadIdx.x == 0) flat[gt[1] + n] = dot / norm;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const float val = g_arena[wt_off + (size_t)k * Np + n] * s - c * v[(size_t)n * K + k];
+            if (direct) gv[(size_t)n * K + k] += val; else gv[(size_t)n * K + k] = val;
+        }
+        if (threadIdx.x == 0) { if (direct) gg[n] += dot / norm; else gg[n] = dot / norm; }
     } else {
-        for (int k = threadIdx.x; k < K; k += blockDim.x) gv[(size_t)n * K + k] = g_arena[wt_off + (size_t)k * Np + n];
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const float val = g_arena[wt_off + (size_t)k * Np + n];
+            if (direct) gv[(size_t)n * K + k] += val; else gv[(size_t)n * K + k] = val;
+        }
     }
-    if (threadIdx.x == 0) flat[gt[2] + n] = g_arena[b_off + n];
+    if (threadIdx.x == 0) { if (direct) gb[n] += g_arena[b_off + n]; else gb[n] = g_arena[b_off + n]; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -335,6 +344,57 @@ __global__ void ray_loss_kernel(const float* __restrict__ image, const float* __
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// deformation-code regulariser (morpheus.py:762-771): mean_c (2 c(t) - c(t - 1/F) - c(t + 1/F))^2 over the 48 code channels,
+// c(.) = MultiCode.sample (models/deform_code.py:20-40: align_corners linear interpolation on three lines [16, S_v]).
+struct CodeTap { int i0, i1; float w0, w1; };
+__device__ __forceinline__ CodeTap code_tap(float t, int S) {
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    const float g = __fsub_rn(__fmul_rn(t, 2.f), 1.f);
+    const float pos = __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), (float)(S - 1));
+    CodeTap c;
+    c.i0 = min(max((int)floorf(pos), 0), S - 1);
+    c.i1 = min(c.i0 + 1, S - 1);
+    c.w1 = pos - (float)c.i0;
+    c.w0 = 1.f - c.w1;
+    if (c.i0 + 1 > S - 1) c.w1 = 0.f;
+    return c;
+}
+// one block of 64 threads; thread = channel (v = tid / 16, c = tid % 16) for tid < 48.  g_out == nullptr: forward (out[0] = loss);
+// else backward: g_code[v][c][.] += g_out[0] * d loss / d line
+__global__ void code_reg_kernel(const float* __restrict__ c0, const float* __restrict__ c1, const float* __restrict__ c2, int S0, int S1, int S2,
+                                const float* __restrict__ t_ptr, float inv_frames, float* __restrict__ out, const float* __restrict__ g_out,
+                                float* __restrict__ g0, float* __restrict__ g1, float* __restrict__ g2) {
+    const int tid = threadIdx.x;
+    float contrib = 0.f;
+    if (tid < 48) {
+        const int v = tid >> 4, c = tid & 15;
+        const int S = v == 0 ? S0 : (v == 1 ? S1 : S2);
+        const float* line = (v == 0 ? c0 : (v == 1 ? c1 : c2)) + (size_t)c * S;
+        const float t = t_ptr[0];
+        const CodeTap a = code_tap(t, S), b = code_tap(__fsub_rn(t, inv_frames), S), d = code_tap(__fadd_rn(t, inv_frames), S);
+        const float va = line[a.i0] * a.w0 + line[a.i1] * a.w1, vb = line[b.i0] * b.w0 + line[b.i1] * b.w1, vd = line[d.i0] * d.w0 + line[d.i1] * d.w1;
+        const float r = 2.f * va - vb - vd;
+        contrib = r * r * (1.0f / 48.0f);
+        if (g_out) {
+            float* gl = (v == 0 ? g0 : (v == 1 ? g1 : g2)) + (size_t)c * S;
+            const float k = g_out[0] * 2.f * r * (1.0f / 48.0f);
+            atomicAdd(gl + a.i0, 2.f * k * a.w0); atomicAdd(gl + a.i1, 2.f * k * a.w1);
+            atomicAdd(gl + b.i0, -k * b.w0); atomicAdd(gl + b.i1, -k * b.w1);
+            atomicAdd(gl + d.i0, -k * d.w0); atomicAdd(gl + d.i1, -k * d.w1);
+        }
+    }
+    if (!g_out) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        __shared__ float sacc[2];
+        if ((tid & 31) == 0) sacc[tid >> 5] = contrib;
+        __syncthreads();
+        if (tid == 0) out[0] = sacc[0] + sacc[1];
+    }
+}
+
 }  // namespace mb
 
 extern "C" int mb_ray_points_forward(const float* rays_o, const float* rays_d, const int64_t* ray_indices, const float* t_starts,
@@ -365,8 +425,8 @@ extern "C" int mb_pack_arena_forward(const int64_t* layer_table, int n_layers, f
 extern "C" int mb_pack_arena_backward(const int64_t* layer_table, const int64_t* grad_table, int n_layers, const float* g_arena, float* flat_grads,
                                       mb_stream_t stream) {
     using namespace mb;
-    if (!layer_table || !grad_table || !g_arena || !flat_grads || n_layers <= 0) { set_error("pack_arena_backward: bad argument"); return MB_EINVAL; }
-    pack_arena_bwd_kernel<<<dim3(128, n_layers), 128, 0, (cudaStream_t)stream>>>(layer_table, grad_table, g_arena, flat_grads);
+    if (!layer_table || !grad_table || !g_arena || n_layers <= 0) { set_error("pack_arena_backward: bad argument"); return MB_EINVAL; }
+    pack_arena_bwd_kernel<<<dim3(128, n_layers), 128, 0, (cudaStream_t)stream>>>(layer_table, grad_table, g_arena, flat_grads, flat_grads == nullptr ? 1 : 0);
     return check_launch("pack_arena_backward");
 }
 
@@ -419,4 +479,14 @@ extern "C" int mb_ray_loss(const float* image, const float* opacity, const float
     ray_loss_kernel<<<min(div_up(N, 256), (uint32_t)mb_sm_count()), 256, 0, (cudaStream_t)stream>>>(image, opacity, depth, gt_rgb, gt_depth, gt_mask, rays_o, rays_d,
                                                                                                      N, w_rgb, w_mask, w_depth, out1, g_image, g_opacity, g_depth);
     return check_launch("ray_loss");
+}
+
+extern "C" int mb_code_reg(const float* const code[3], const int code_len[3], const float* t_dev, float inv_frames, float* out1, const float* g_out1,
+                           float* const g_code[3], mb_stream_t stream) {
+    using namespace mb;
+    if (!code || !code_len || !t_dev || (!out1 && !g_out1)) { set_error("code_reg: null argument"); return MB_EINVAL; }
+    if (g_out1 && !g_code) { set_error("code_reg: backward needs g_code"); return MB_EINVAL; }
+    code_reg_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(code[0], code[1], code[2], code_len[0], code_len[1], code_len[2], t_dev, inv_frames, out1, g_out1,
+                                                         g_out1 ? g_code[0] : nullptr, g_out1 ? g_code[1] : nullptr, g_out1 ? g_code[2] : nullptr);
+    return check_launch("code_reg");
 }

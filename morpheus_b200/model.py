@@ -251,6 +251,36 @@ class _PoseRays(torch.autograd.Function):
         return g_pose, g_o, g_d, None
 
 
+class _CodeReg(torch.autograd.Function):
+    """loss_code of render_rays (morpheus.py:762-771): mean (2 c(t) - c(t - 1/F) - c(t + 1/F))^2 over the 48 code channels in one
+    launch (and one backward launch) instead of ~80 eager ops (three MultiCode.sample calls with index_put backward sorts)."""
+
+    @staticmethod
+    def forward(ctx, t_dev, inv_frames, sinks, v0, v1, v2):
+        vols = [v.detach() for v in (v0, v1, v2)]
+        out = torch.empty(1, device=v0.device, dtype=torch.float32)
+        codes = (_lib.C.c_void_p * 3)(*[v.data_ptr() for v in vols])
+        lens = (_lib.C.c_int * 3)(*[int(v.shape[2]) for v in vols])
+        check(_lib.lib().mb_code_reg(codes, lens, ptr(t_dev), _lib.C.c_float(inv_frames), ptr(out), None, None, stream()), 'code_reg')
+        ctx.save_for_backward(t_dev, v0, v1, v2)
+        ctx.inv_frames, ctx.sinks = inv_frames, sinks
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        t_dev, v0, v1, v2 = ctx.saved_tensors
+        vols = [v0, v1, v2]
+        grads = ctx.sinks if ctx.sinks is not None else [torch.zeros_like(v) for v in vols]
+        codes = (_lib.C.c_void_p * 3)(*[v.data_ptr() for v in vols])
+        lens = (_lib.C.c_int * 3)(*[int(v.shape[2]) for v in vols])
+        gptrs = (_lib.C.c_void_p * 3)(*[x.data_ptr() for x in grads])
+        check(_lib.lib().mb_code_reg(codes, lens, ptr(t_dev), _lib.C.c_float(ctx.inv_frames), None, ptr(g.reshape(1).contiguous().float()), gptrs,
+                                     stream()), 'code_reg(backward)')
+        if ctx.sinks is not None:
+            return None, None, None, None, None, None
+        return None, None, None, grads[0], grads[1], grads[2]
+
+
 # ------------------------------------------------------------------------------------------------
 # parameter arena: weight_norm + transpose + pad of the 18 dense layers in ONE launch (and one backward launch)
 # ------------------------------------------------------------------------------------------------
@@ -270,10 +300,16 @@ class _PackArena(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_arena):
         tensors = ctx.saved_tensors
+        ctx.owner._arena_cache = None      # this graph is consumed: the next query packs again
+        sink = ctx.owner._direct_grad_table(tensors)
+        if sink is not None:
+            # gradient sink (train.FlatAdam): accumulate straight into the parameters' .grad views of the flat gradient buffer
+            check(_lib.lib().mb_pack_arena_backward(ptr(ctx.table), ptr(sink), ctx.table.shape[0], ptr(g_arena.contiguous()), None, stream()),
+                  'pack_arena_backward')
+            return (None, None, None, None) + (None,) * len(tensors)
         flat = torch.empty(ctx.n_grad, device=g_arena.device, dtype=torch.float32)
         check(_lib.lib().mb_pack_arena_backward(ptr(ctx.table), ptr(ctx.gtable), ctx.table.shape[0], ptr(g_arena.contiguous()), ptr(flat),
                                                 stream()), 'pack_arena_backward')
-        ctx.owner._arena_cache = None      # this graph is consumed: the next query packs again
         grads, off = [], 0
         for t in tensors:
             grads.append(flat[off:off + t.numel()].view(t.shape))
@@ -291,7 +327,7 @@ class _FieldQuery(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg, x, t, light, topo_in, arena, emb_sdf, emb_col, code0, code1, code2, beta):
-        flags, shading, ratio, n_levels, n_freq, offsets, bound, S, H, tcws = cfg
+        flags, shading, ratio, n_levels, n_freq, offsets, bound, S, H, tcws, sinks = cfg
         M = x.shape[0]
         dev = x.device
         x = x.contiguous().float()
@@ -342,7 +378,7 @@ class _FieldQuery(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_sdf, g_sigma, g_color, g_normal, g_raw, g_deform, g_topo):
-        flags, shading, ratio, n_levels, n_freq, offsets, bound, S, H, tcws = ctx.cfg
+        flags, shading, ratio, n_levels, n_freq, offsets, bound, S, H, tcws, sinks = ctx.cfg
         x, t, light, topo_in, arena, emb_sdf, emb_col, c0, c1, c2, beta_d, deform, topo, normal_raw = ctx.saved_tensors
         M = x.shape[0]
         codes = [c0, c1, c2]
@@ -366,9 +402,12 @@ class _FieldQuery(torch.autograd.Function):
         G.g_sdf, G.g_sigma, G.g_color, G.g_normal, G.g_normal_raw, G.g_deform, G.g_topo = map(ptr, (g_sdf, g_sigma, g_color, g_normal, g_raw, g_deform, g_topo))
         G.deform, G.topo, G.normal_raw = ptr(deform), ptr(topo), ptr(normal_raw)
         g_arena = torch.zeros_like(arena)
-        g_es = torch.zeros_like(emb_sdf)
-        g_ec = torch.zeros_like(emb_col)
-        g_codes = [torch.zeros_like(c) for c in codes]
+        if sinks is not None:       # accumulate (red.global.add) straight into the parameters' .grad: no zero-fill, no autograd adds
+            g_es, g_ec, g_codes = sinks[0], sinks[1], [g.view(c.shape) for g, c in zip(sinks[2:], codes)]
+        else:
+            g_es = torch.zeros_like(emb_sdf)
+            g_ec = torch.zeros_like(emb_col)
+            g_codes = [torch.zeros_like(c) for c in codes]
         g_beta = torch.zeros(1, device=x.device, dtype=torch.float32)
         g_x = torch.empty_like(x)
         g_topo_in = torch.empty_like(topo_in) if topo_in is not None else None
@@ -415,6 +454,8 @@ class _FieldQuery(torch.autograd.Function):
                                                            ptr(tcw_t), ptr(tabs[1]), ptr(g_arena), gcode_ptrs, ptr(g_x), stream()),
                       'field_backward_warp_tc')
             ctx.stash = None
+        if sinks is not None:
+            return (None, g_x, None, None, g_topo_in, g_arena, None, None, None, None, None, g_beta.reshape(()))
         gc = [g.reshape(s) for g, s in zip(g_codes, ctx.shapes)]
         return (None, g_x, None, None, g_topo_in, g_arena, g_es, g_ec, gc[0], gc[1], gc[2], g_beta.reshape(()))
 
@@ -457,6 +498,8 @@ class scene_representation(nn.Module):
         self.sdf2density = LaplaceDensity({'beta': 0.1})
         self._arena_cache = None
         self._pack_tab = None
+        self._sink_tab = None
+        self.grad_sink = False      # set by train.FlatAdam: kernels accumulate parameter gradients straight into .grad
 
     # -- packed parameters ----------------------------------------------------------------------------
     def _pack_inputs(self):
@@ -488,6 +531,34 @@ class scene_representation(nn.Module):
             dev = tensors[0].device
             self._pack_tab = (key, torch.tensor(rows, dtype=torch.int64, device=dev), torch.tensor(grows, dtype=torch.int64, device=dev), off)
         return self._pack_tab[1:]
+
+    def _direct_grad_table(self, tensors):
+        """with `grad_sink` set (train.FlatAdam): device table of the parameters' .grad addresses for mb_pack_arena_backward's
+        direct mode ({gv, gg, gb, 0} per layer), or None when any .grad is missing / the sink is off"""
+        if not self.grad_sink or any(t.grad is None or not t.grad.is_contiguous() for t in tensors):
+            return None
+        key = tuple(t.grad.data_ptr() for t in tensors)
+        if self._sink_tab is None or self._sink_tab[0] != key:
+            rows, it = [], iter(tensors)
+            for mlp in (self.deform_net, self.topo_net, self.sdf_net, self.color_net):
+                for _ in mlp.net:
+                    if mlp.uses_weight_norm:
+                        v, g, b = next(it), next(it), next(it)
+                        rows.append([v.grad.data_ptr(), g.grad.data_ptr(), b.grad.data_ptr(), 0])
+                    else:
+                        w, b = next(it), next(it)
+                        rows.append([w.grad.data_ptr(), 0, b.grad.data_ptr(), 0])
+            self._sink_tab = (key, torch.tensor(rows, dtype=torch.int64, device=tensors[0].device))
+        return self._sink_tab[1]
+
+    def _sinks(self):
+        """.grad tensors the field kernels may accumulate into directly (hash tables, code lines) when `grad_sink` is set"""
+        if not self.grad_sink or not torch.is_grad_enabled():
+            return None
+        ps = [self.encoder.embeddings, self.encoder_c.embeddings] + list(self.deform_code.volumes)
+        if any(p.grad is None or not p.grad.is_contiguous() or not p.requires_grad for p in ps):
+            return None
+        return [p.grad for p in ps]
 
     def packed_arena(self):
         """(flat effective-weight arena, tensor-core operand tables).  Packed by ONE launch (differentiable through
@@ -549,7 +620,7 @@ class scene_representation(nn.Module):
                     self._arena_cache = (self._arena_cache[0], arena, tcw)
         elif _lib.USE_TC:
             tcw = self._pack_tc(arena.detach())
-        cfg = cfg + (tcw,)
+        cfg = cfg + (tcw, self._sinks())
         v = self.deform_code.volumes
         return _FieldQuery.apply(cfg, x, t, light, topo_in, arena, self.encoder.embeddings, self.encoder_c.embeddings,
                                  v[0], v[1], v[2], self.sdf2density.get_beta())
@@ -557,6 +628,16 @@ class scene_representation(nn.Module):
     # -- reference API --------------------------------------------------------------------------------
     def get_deform_code(self, t, app=False):
         return self.deform_code.sample(t)
+
+    def code_regulariser(self, t, num_frames):
+        """morpheus.py:766-771 on the three code lines: mean (2 c(t) - c(t - 1/F) - c(t + 1/F))^2, fused (one launch each way)"""
+        t_dev = t.reshape(-1)[:1].contiguous().float()
+        v = self.deform_code.volumes
+        if not v[0].is_cuda:
+            codes = self.get_deform_code(torch.cat([t_dev.view(1, 1), t_dev.view(1, 1) - 1 / num_frames, t_dev.view(1, 1) + 1 / num_frames], dim=0))
+            return torch.square(2 * codes[0:1] - codes[1:2] - codes[2:3]).mean()
+        sinks = self._sinks()
+        return _CodeReg.apply(t_dev, 1.0 / num_frames, sinks[2:] if sinks is not None else None, v[0], v[1], v[2])
 
     def get_RT(self, frame_ids):
         frame_ids = frame_ids.squeeze()

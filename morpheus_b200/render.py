@@ -298,10 +298,7 @@ class Renderer:
                 normals_perturb, _ = model.normal(xyzs_perturb, topo=None, cano=cano)
                 results['loss_normal_perturb'] = (normals - normals_perturb).abs().mean()
             if tr['code_reg'] > 0 and not cano:
-                ts = time_step[:1]
-                # morpheus.py:766-771: code(t), code(t - 1/F), code(t + 1/F) -- sampled in ONE batched call (same arithmetic per row)
-                codes = model.get_deform_code(torch.cat([ts, ts - 1 / self.num_frames, ts + 1 / self.num_frames], dim=0))
-                results['loss_code'] = torch.square(2 * codes[0:1] - codes[1:2] - codes[2:3]).mean()
+                results['loss_code'] = model.code_regulariser(time_step[:1], self.num_frames)      # morpheus.py:762-771, one launch
             if tr.get('normal_smoothness', 0) > 0:
                 results['normal_reg'] = self.get_normal_smoothness_loss(rays_o, rays_d, rays_t, depth)      # morpheus.py:778-785
             if rays_depth is not None:

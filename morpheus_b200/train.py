@@ -189,6 +189,7 @@ class FlatAdam:
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # device-side step count (CUDA-graph replayable)
         self.params = plist
         self.model = model
+        model.grad_sink = True      # every .grad is a view of self.grad: the kernels accumulate into it directly
         self.current_learning_rate = lr
 
     def set_group_lr(self, name, lr):

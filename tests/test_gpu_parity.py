@@ -736,3 +736,36 @@ def test_forward_only_consumers(dev):
     a = R.render_image(o.to(dev), d.to(dev), t.to(dev), ids.to(dev), chunk=128, jitter=None, shading='albedo')
     assert a['image'].shape == (300, 3) and a['depth'].shape == (300,) and torch.isfinite(a['image']).all()
     assert m.training is False
+
+
+def test_gradient_sinks_and_code_regulariser(dev):
+    """train.FlatAdam switches the model's gradient sink on: the field kernels, mb_pack_arena_backward (direct mode) and mb_code_reg
+    accumulate straight into the flat gradient buffer.  Same step with the sink off (plain autograd accumulation) -> same gradients;
+    fused code regulariser == three MultiCode.sample calls (morpheus.py:766-771)."""
+    from morpheus_b200 import train as mtrain
+    from morpheus_b200.nerfacc_compat import OccGridEstimator
+    from morpheus_b200.rays import synthetic_real_view_batch
+    from morpheus_b200.render import Renderer
+    from oracle.fields import init_reference_like_state
+    sd = init_reference_like_state(200, seed=17, randomize=True, emb_scale=0.05, sphere=True)
+    tr = dict(mtrain.DEFAULT_TRAIN_CFG)
+    cfg = {'model': {'bg_radius': 1.4, 'activation': 'exp'}, 'render': {'step_size': 0.01}, 'train': tr}
+    batch = {k: v.to(dev) for k, v in synthetic_real_view_batch(96, seed=5, frame=40).items()}
+    grads, losses = [], []
+    for sink in (False, True):
+        m = make_model(sd, 1.0, dev).train()
+        R = Renderer(m, OccGridEstimator(torch.tensor([-1.01] * 3 + [1.01] * 3), 128).to(dev), cfg, 200, uniform_samples=24)
+        opt = mtrain.FlatAdam(m, tr['lr'])
+        m.grad_sink = sink
+        torch.manual_seed(3)
+        losses.append(float(mtrain.train_step_compute(R, opt, batch, tr)))
+        torch.cuda.synchronize()
+        grads.append(opt.grad.clone())
+        # fused code regulariser vs the eager formulation
+        t = torch.full((1, 1), 40 / 200, device=dev)
+        codes = m.get_deform_code(torch.cat([t, t - 1 / 200, t + 1 / 200], dim=0))
+        ref = torch.square(2 * codes[0:1] - codes[1:2] - codes[2:3]).mean()
+        assert abs(float(m.code_regulariser(t, 200)) - float(ref)) < 1e-6 * max(1.0, abs(float(ref)))
+    assert abs(losses[0] - losses[1]) < 1e-6 * max(1.0, abs(losses[0]))
+    assert float(grads[0].abs().max()) > 0
+    assert rel_l2(cpu(grads[1]), cpu(grads[0])) < 1e-5
