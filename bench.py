@@ -192,7 +192,11 @@ def main():
     host = []
     for s in range(total_steps):
         b = synthetic_real_view_batch(N_RAYS, seed=1000 + s, frame=(37 * s) % NUM_FRAMES)
-        host.append({k: v[rank * n_local:(rank + 1) * n_local].contiguous().pin_memory() for k, v in b.items()})
+        shard = {k: v[rank * n_local:(rank + 1) * n_local].contiguous().pin_memory() for k, v in b.items()}
+        if world > 1:      # global normaliser of the SDF band loss (utils.py:107), known to whoever shards the batch: mean over ranks of
+            # count_nonzero(depth[ray_indices]) = (#rays with depth) * S / world  (see render.global_count)
+            shard['n_depth'] = (torch.count_nonzero(b['depth']).float() * N_SAMPLES / world).reshape(1).pin_memory()
+        host.append(shard)
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 

@@ -176,7 +176,7 @@ __device__ __noinline__ void grid_bwd_samples(const GridCtx g, const float* __re
 __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_field_params p, const mb_field_io io, const mb_field_grads gr,
                                                                      const uint8_t* __restrict__ tcw_f, const uint32_t* __restrict__ off_f,
                                                                      const uint8_t* __restrict__ tcw_d, const uint32_t* __restrict__ off_d,
-                                                                     const int accumulate) {
+                                                                     const int accumulate, const int nsub) {
     extern __shared__ __align__(128) uint8_t smem[];
     float* sp = reinterpret_cast<float*>(smem + Smem::SP);
     float* stopo = reinterpret_cast<float*>(smem + Smem::STOPO);
@@ -217,7 +217,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_holder;
-    const uint32_t n_tiles = div_up(io.M, TM);
+    // a tile = nsub sub-tiles = 16 * nsub samples (<= 128): one gradient scale and one accumulator flush per tile; the host picks a
+    // smaller tile for small M so that the persistent grid stays balanced (ray-sharded runs: 512 rays per GPU at 8 GPUs)
+    const uint32_t TMt = 16u * (uint32_t)nsub;
+    const uint32_t n_tiles = div_up(io.M, TMt);
     const uint32_t my_tiles = (blockIdx.x < n_tiles) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     // weight slabs: forward table rows 12, 13 (sdf0: 5 x 4096 B, sdf1: 4 x 4096 B); dgrad table rows 1, 0 (sdf1: 4 x 4096 B, sdf0: 4 x 5120 B)
     const uint32_t f0_off = off_f[3 * 12], f1_off = off_f[3 * 13], d1_off = off_d[3 * 1], d0_off = off_d[3 * 0];
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
                 bulk_g2s(smem + Smem::W + stg * STAGE_BYTES, src, bytes, full + stg);
                 loads++;
             };
-            for (uint64_t u = 0; u < (uint64_t)my_tiles * NSUB; u++) {
+            for (uint64_t u = 0; u < (uint64_t)my_tiles * (uint64_t)nsub; u++) {
                 for (uint32_t st = 0; st < 5; st++) load(tcw_f + f0_off + (size_t)st * 4096, 4096);
                 for (uint32_t st = 0; st < 4; st++) load(tcw_f + f1_off + (size_t)st * 4096, 4096);
                 for (uint32_t st = 0; st < 4; st++) load(tcw_d + d1_off + (size_t)st * 4096, 4096);
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
                 }
             };
             for (uint32_t it = 0; it < my_tiles; it++) {
-                for (int j = 0; j < NSUB; j++) {
+                for (int j = 0; j < nsub; j++) {
                     wait_z(); gemm_ring(s0_base, S0_LO, 5, 64, 64); umma_commit(acc_ready);                                   // A1 = S0 W0^T
                     wait_z(); gemm_ring(x0_base, X0_LO, 4, 64, 64); umma_commit(acc_ready);                                    // A2 = A1 W1^T
                     wait_z(); wgrad(x0_base, X0_LO, 192, j == 0); gemm_ring(dz_base, X_LO, 4, 64, 64); umma_commit(acc_ready);  // dW1, dA1
@@ -311,8 +314,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
             store_core(X0, tid, 8, one8, X0_LO, PITCH);
         }
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const uint32_t m0 = tile * TM;
-            const int nv = (int)min((uint32_t)TM, io.M - m0);
+            const uint32_t m0 = tile * TMt;
+            const int nv = (int)min(TMt, io.M - m0);
             // ---- per-sample inputs, upstream -> d/d(sdf) of the six queries ----
             for (int idx = tid; idx < 3 * TM; idx += NWORK) {
                 const int mm = idx / 3, a = idx - mm * 3;
@@ -390,7 +393,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
             FD_PHASE(0);      // tile prologue
 
 #pragma unroll 1
-            for (int j = 0; j < NSUB; j++) {
+            for (int j = 0; j < nsub; j++) {
                 // ---- rows of the sub-tile: sample s = 16 j + r / 6, query r % 6 ----
                 if (tid < RT) {
                     const int s = 16 * j + tid / 6, qq = tid % 6;
@@ -642,6 +645,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_bwd_fd_tc_kernel(const mb_f
 
 extern "C" int mb_field_backward_fd_tc(const mb_field_params* p, const mb_field_io* io, const mb_field_grads* g, const void* tc_weights,
                                        const uint32_t* tc_off, const void* tc_weights_t, const uint32_t* tc_off_t, int accumulate, mb_stream_t stream) {
+    // (declared with C linkage in include/morpheus_b200.h)
     using namespace mb;
     if (!p || !io || !g || !tc_weights || !tc_off || !tc_weights_t || !tc_off_t) { set_error("field_backward_fd_tc: null argument"); return MB_EINVAL; }
     if (io->M == 0) return MB_OK;
@@ -664,10 +668,13 @@ extern "C" int mb_field_backward_fd_tc(const mb_field_params* p, const mb_field_
         if (e != cudaSuccess) { set_error("field_backward_fd_tc: cannot reserve %zu B smem: %s", smem, cudaGetErrorString(e)); return MB_ECUDA; }
         attr_set = true;
     }
-    const uint32_t n_tiles = div_up(io->M, tcf::TM);
-    const uint32_t grid = min(n_tiles, (uint32_t)mb_sm_count() * 2u);
+    const uint32_t slots = (uint32_t)mb_sm_count() * 2u;
+    const uint32_t n128 = div_up(io->M, tcf::TM);
+    const int nsub = n128 >= 4 * slots ? 8 : (n128 >= 2 * slots ? 4 : 2);       // samples per tile: 128 / 64 / 32
+    const uint32_t n_tiles = div_up(io->M, 16u * (uint32_t)nsub);
+    const uint32_t grid = min(n_tiles, slots);
     tcf::field_bwd_fd_tc_kernel<<<grid, tcf::NTHREADS, smem, (cudaStream_t)stream>>>(*p, *io, *g, (const uint8_t*)tc_weights, tc_off,
-                                                                                     (const uint8_t*)tc_weights_t, tc_off_t, accumulate);
+                                                                                     (const uint8_t*)tc_weights_t, tc_off_t, accumulate, nsub);
     return check_launch("field_backward_fd_tc");
 }
 

@@ -323,6 +323,11 @@ class GraphedStep:
         """global count of samples with a depth observation (utils.py:107 normaliser) for the fixed-S sampler:
         (#rays with depth > 0) * S, averaged over ranks (see render.global_count)"""
         if self.world > 1:
+            if 'n_depth' in self.batch:
+                # the data pipeline that shards the ray batch knows the GLOBAL number of samples with a depth observation: it ships
+                # it with the shard (4 bytes), so the step needs no extra collective and no eager launches before the graph
+                self.renderer.sdf_count_override.copy_(self.batch['n_depth'].reshape(()))
+                return
             from .render import global_count
             S = self.renderer.uniform_samples
             cnt = global_count(torch.count_nonzero(self.batch['depth']) * S, self.world)
