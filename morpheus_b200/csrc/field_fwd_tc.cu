@@ -236,17 +236,20 @@ __global__ void __launch_bounds__(NTHREADS, 2) field_fwd_tc_kernel(const mb_fiel
         auto bar_workers = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory"); };
 
         // SDF-net input at point pt[3]: cores 0-4 freq, 5-8 grid, 9 topo
+        // SDF-net input: the two warpgroups split the 16 grid levels 8 / 8 (each level is one dependent L2 round trip) and the
+        // frequency features 2 axes / 1 axis + pad + topo
         auto build_sdf_input = [&](const float* pt3, const float* topo2) {
             const float pnt[3] = {pt3[m], pt3[TM + m], pt3[2 * TM + m]};
             if (wg == 0) {
 #pragma unroll 1
-                for (int a = 0; a < 3; a++) freq_axis_tc(A, m, a, pt3[a * TM + m], (int)p.n_freq);
-                store_one(A, m, 39, 0.f);
-                gather_levels_tc(A, m, 40, gs, 0, 4, pnt);
+                for (int a = 0; a < 2; a++) freq_axis_tc(A, m, a, pt3[a * TM + m], (int)p.n_freq);
+                gather_levels_tc(A, m, 40, gs, 0, 8, pnt);
             } else {
-                gather_levels_tc(A, m, 40, gs, 4, 12, pnt);
+                freq_axis_tc(A, m, 2, pt3[2 * TM + m], (int)p.n_freq);
+                store_one(A, m, 39, 0.f);
                 float v[8] = {topo2[m], topo2[TM + m], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 store_core(A, m, 9, v);
+                gather_levels_tc(A, m, 40, gs, 8, 8, pnt);
             }
         };
 
