@@ -99,7 +99,8 @@ __device__ __noinline__ void grid_bwd_samples(const GridCtx g, const float* __re
     uint32_t cidx[8];
     float2 cv[8];
     float acc[16];
-#pragma unroll 1
+    float dxr[6][3];
+#pragma unroll
     for (int i = 0; i < 6; i++) {
         const int r = s * 6 + i;
         float dx[3] = {0.f, 0.f, 0.f};
@@ -157,19 +158,24 @@ __device__ __noinline__ void grid_bwd_samples(const GridCtx g, const float* __re
                 }
             }
         }
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-#pragma unroll
-            for (int d = 0; d < 3; d++) dx[d] += __shfl_xor_sync(0xffffffffu, dx[d], o);
-        }
-        if (l == 0) {
-#pragma unroll
-            for (int d = 0; d < 3; d++) gp[d * RT + r] += dx[d];
-        }
+        dxr[i][0] = dx[0]; dxr[i][1] = dx[1]; dxr[i][2] = dx[2];
     }
     if (have) {
 #pragma unroll
         for (int c = 0; c < 8; c++) red_add2(gt + 2 * cidx[c], acc[2 * c], acc[2 * c + 1]);
+    }
+    // d/d(point) summed over the 16 levels (lanes of a half-warp) once, after the row loop (no warp-synchronous step per row)
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) dxr[i][d] += __shfl_xor_sync(0xffffffffu, dxr[i][d], o);
+        }
+        if (l == 0) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) gp[d * RT + s * 6 + i] += dxr[i][d];
+        }
     }
 }
 
