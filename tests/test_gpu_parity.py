@@ -769,3 +769,59 @@ def test_gradient_sinks_and_code_regulariser(dev):
     assert abs(losses[0] - losses[1]) < 1e-6 * max(1.0, abs(losses[0]))
     assert float(grads[0].abs().max()) > 0
     assert rel_l2(cpu(grads[1]), cpu(grads[0])) < 1e-5
+
+
+def test_edge_cases_empty_tiny_and_errors(dev):
+    """Edge cases the reference handles (or trips over): empty sample set -> white image / zero depth (morpheus.py:663-670);
+    M = 0 launches are no-ops; null pointers surface as RuntimeError (the reference raises from TORCH_CHECK); tiny and
+    non-multiple-of-16 query counts through the FD backward kernel (partial sub-tiles) match the fp32 SIMT engine."""
+    import ctypes as C
+    from morpheus_b200 import _lib
+    from morpheus_b200.nerfacc_compat import OccGridEstimator
+    from morpheus_b200.render import Renderer
+    from oracle.fields import init_reference_like_state
+    sd = init_reference_like_state(200, seed=8, randomize=True, emb_scale=0.2)
+    m = make_model(sd, 1.0, dev).train()
+    cfg = {'model': {'bg_radius': 1.4, 'activation': 'exp'}, 'render': {'step_size': 0.01},
+           'train': {'ori_weight': 0.0, 'normal_smooth_3d': 0.0, 'code_reg': 0.0, 'trunc': 0.1}}
+    est = OccGridEstimator(torch.tensor([-1.01] * 3 + [1.01] * 3), 128).to(dev)      # binaries all False: every ray is empty
+    R = Renderer(m, est, cfg, 200)
+    N = 7
+    o = torch.tensor([[0.0, 0.0, 2.5]]).repeat(N, 1).to(dev)
+    d = torch.tensor([[0.0, 0.0, -1.0]]).repeat(N, 1).to(dev)
+    out = R.render_rays(o[None], d[None], torch.full((1, N, 1), 0.1, device=dev), torch.zeros(1, N, 1, dtype=torch.long, device=dev))
+    assert out['image'].shape == (1, N, 3) and float((out['image'] - 1).abs().max()) == 0.0
+    assert out['depth'].shape == (1, N) and float(out['depth'].abs().max()) == 0.0 and out['sdf'] is None
+    # M = 0 / N = 0 launches
+    L = _lib.lib()
+    assert L.mb_ray_points_forward(None, None, None, None, None, 0, None, _lib.stream()) == 0
+    assert L.mb_sdf_loss_forward(_lib.ptr(o), _lib.ptr(o), _lib.ptr(o), _lib.ptr(o), None, _lib.ptr(o), 0, C.c_float(0.1), _lib.ptr(o), _lib.stream()) == 0
+    assert L.mb_pose_rays_forward(None, None, None, None, 0, None, None, _lib.stream()) == 0
+    # null pointers -> error code + message -> RuntimeError in the Python shim
+    rc = L.mb_ray_points_forward(None, None, None, None, None, 5, None, _lib.stream())
+    assert rc != 0 and b'null' in L.mb_last_error()
+    with pytest.raises(RuntimeError):
+        _lib.check(L.mb_pack_arena_forward(None, 18, None, _lib.stream()), 'pack_arena_forward')
+    with pytest.raises(RuntimeError):
+        _lib.check(L.mb_field_backward_fd_tc(None, None, None, None, None, None, None, 0, _lib.stream()), 'field_backward_fd_tc')
+    with pytest.raises(RuntimeError):
+        m.normal(torch.zeros(0, 3, device=dev), topo=None)          # empty query: explicit error instead of the reference's NameError
+    # tiny / ragged FD queries: tensor-core FD kernel vs SIMT engine
+    g = torch.Generator().manual_seed(2)
+    old = (_lib.USE_TC, _lib.USE_TC_BWD, _lib.USE_TC_BWD_SDF)
+    try:
+        for M in (1, 17, 130):
+            x = ((torch.rand(M, 3, generator=g) * 2 - 1) * 0.9).to(dev)
+            w = torch.randn(M, 3, generator=g).to(dev)
+            res = {}
+            for tc in (False, True):
+                _lib.USE_TC, _lib.USE_TC_BWD, _lib.USE_TC_BWD_SDF = True, tc, tc
+                mm = make_model(sd, 1.0, dev).train()
+                xg = x.clone().requires_grad_(True)
+                n, raw = mm.normal(xg, topo=None)
+                (n * w).sum().backward()
+                res[tc] = (xg.grad.clone(), mm.encoder.embeddings.grad.clone(), mm.sdf_net.net[0].weight.grad.clone())
+            for a, b in zip(res[True], res[False]):
+                assert rel_l2(cpu(a), cpu(b)) < 3e-4, M
+    finally:
+        _lib.USE_TC, _lib.USE_TC_BWD, _lib.USE_TC_BWD_SDF = old
