@@ -320,7 +320,7 @@ def main():
                 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                 'config': dict(workload_config(world), cuda_graph=(not args.no_graph), full_step=bool(args.full_step)), 'clocks': clocks,
                 'e2e': {'value': e2e_val, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
-                'gpu_launches': launches, 'kernels': kern, 'final_loss': last_loss,
+                'gpu_launches': (launches * args.steps if launches else launches), 'gpu_launches_per_step': launches, 'kernels': kern, 'final_loss': last_loss,
                 'roofline': roof, 'rooflines': rooflines,
                 'cpu_baseline': {'value': cpu_val, 'unit': 'rays/s', 'cores': cpu_threads(), 'kind': 'port',
                                  'sample': f'64 rays x {N_SAMPLES} samples (1/64 of the step), fwd+bwd+Adam, {args.cpu_baseline_steps} timed steps after 1 warm-up, oracle port on torch CPU'}}
