@@ -193,16 +193,16 @@ def vae_encode_moments(sd, img):
 
 class _precision:
     """'fp32': true fp32 convolutions / matmuls (cuDNN would otherwise pick TF32 for convs by default, ~2e-3 error on the
-    SDS gradient); 'tf32': allow TF32 tensor-core paths (what stock PyTorch does for the reference on Ampere+); 'bf16': autocast."""
+    SDS gradient); 'reference': exactly what stock PyTorch gives the reference on Ampere+ GPUs (its `fp16: False` path): TF32
+    cuDNN convolutions, fp32 matmuls; 'tf32': TF32 for both; 'bf16': autocast."""
 
     def __init__(self, mode):
         self.mode = mode
 
     def __enter__(self):
         self.prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-        allow = self.mode != 'fp32'
-        torch.backends.cudnn.allow_tf32 = allow
-        torch.backends.cuda.matmul.allow_tf32 = allow
+        torch.backends.cudnn.allow_tf32 = self.mode != 'fp32'
+        torch.backends.cuda.matmul.allow_tf32 = self.mode not in ('fp32', 'reference')
 
     def __exit__(self, *exc):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self.prev

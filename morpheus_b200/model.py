@@ -231,8 +231,9 @@ class _PoseRays(torch.autograd.Function):
         frame_ids = frame_ids.contiguous().long()
         N = rays_o.shape[0]
         o2, d2 = torch.empty_like(rays_o), torch.empty_like(rays_d)
-        check(_lib.lib().mb_pose_rays_forward(ptr(pose.detach()), ptr(frame_ids), ptr(rays_o), ptr(rays_d), N, ptr(o2), ptr(d2), stream()),
-              'pose_rays_forward')
+        with _lib.timed('pose_rays_fwd'):
+            check(_lib.lib().mb_pose_rays_forward(ptr(pose.detach()), ptr(frame_ids), ptr(rays_o), ptr(rays_d), N, ptr(o2), ptr(d2), stream()),
+                  'pose_rays_forward')
         ctx.save_for_backward(pose, rays_d, frame_ids)
         ctx.set_materialize_grads(False)
         return o2, d2
@@ -246,8 +247,9 @@ class _PoseRays(torch.autograd.Function):
         g_d = torch.empty_like(rays_d) if ctx.needs_input_grad[2] else None
         g_o2 = g_o2.contiguous().float() if g_o2 is not None else None
         g_d2 = g_d2.contiguous().float() if g_d2 is not None else None
-        check(_lib.lib().mb_pose_rays_backward(ptr(pose.detach()), ptr(frame_ids), ptr(rays_d), ptr(g_o2), ptr(g_d2), N, ptr(g_pose), ptr(g_o), ptr(g_d),
-                                               stream()), 'pose_rays_backward')
+        with _lib.timed('pose_rays_bwd'):
+            check(_lib.lib().mb_pose_rays_backward(ptr(pose.detach()), ptr(frame_ids), ptr(rays_d), ptr(g_o2), ptr(g_d2), N, ptr(g_pose), ptr(g_o), ptr(g_d),
+                                                   stream()), 'pose_rays_backward')
         return g_pose, g_o, g_d, None
 
 
@@ -261,7 +263,8 @@ class _CodeReg(torch.autograd.Function):
         out = torch.empty(1, device=v0.device, dtype=torch.float32)
         codes = (_lib.C.c_void_p * 3)(*[v.data_ptr() for v in vols])
         lens = (_lib.C.c_int * 3)(*[int(v.shape[2]) for v in vols])
-        check(_lib.lib().mb_code_reg(codes, lens, ptr(t_dev), _lib.C.c_float(inv_frames), ptr(out), None, None, stream()), 'code_reg')
+        with _lib.timed('code_reg_fwd'):
+            check(_lib.lib().mb_code_reg(codes, lens, ptr(t_dev), _lib.C.c_float(inv_frames), ptr(out), None, None, stream()), 'code_reg')
         ctx.save_for_backward(t_dev, v0, v1, v2)
         ctx.inv_frames, ctx.sinks = inv_frames, sinks
         return out[0]
@@ -274,8 +277,9 @@ class _CodeReg(torch.autograd.Function):
         codes = (_lib.C.c_void_p * 3)(*[v.data_ptr() for v in vols])
         lens = (_lib.C.c_int * 3)(*[int(v.shape[2]) for v in vols])
         gptrs = (_lib.C.c_void_p * 3)(*[x.data_ptr() for x in grads])
-        check(_lib.lib().mb_code_reg(codes, lens, ptr(t_dev), _lib.C.c_float(ctx.inv_frames), None, ptr(g.reshape(1).contiguous().float()), gptrs,
-                                     stream()), 'code_reg(backward)')
+        with _lib.timed('code_reg_bwd'):
+            check(_lib.lib().mb_code_reg(codes, lens, ptr(t_dev), _lib.C.c_float(ctx.inv_frames), None, ptr(g.reshape(1).contiguous().float()), gptrs,
+                                         stream()), 'code_reg(backward)')
         if ctx.sinks is not None:
             return None, None, None, None, None, None
         return None, None, None, grads[0], grads[1], grads[2]
@@ -292,7 +296,8 @@ class _PackArena(torch.autograd.Function):
     @staticmethod
     def forward(ctx, owner, table, gtable, n_grad, *tensors):
         arena = torch.empty(packing.ARENA_FLOATS, device=tensors[0].device, dtype=torch.float32)
-        check(_lib.lib().mb_pack_arena_forward(ptr(table), table.shape[0], ptr(arena), stream()), 'pack_arena_forward')
+        with _lib.timed('pack_arena_fwd'):
+            check(_lib.lib().mb_pack_arena_forward(ptr(table), table.shape[0], ptr(arena), stream()), 'pack_arena_forward')
         ctx.owner, ctx.table, ctx.gtable, ctx.n_grad = owner, table, gtable, n_grad
         ctx.save_for_backward(*tensors)
         return arena
@@ -304,12 +309,14 @@ class _PackArena(torch.autograd.Function):
         sink = ctx.owner._direct_grad_table(tensors)
         if sink is not None:
             # gradient sink (train.FlatAdam): accumulate straight into the parameters' .grad views of the flat gradient buffer
-            check(_lib.lib().mb_pack_arena_backward(ptr(ctx.table), ptr(sink), ctx.table.shape[0], ptr(g_arena.contiguous()), None, stream()),
-                  'pack_arena_backward')
+            with _lib.timed('pack_arena_bwd'):
+                check(_lib.lib().mb_pack_arena_backward(ptr(ctx.table), ptr(sink), ctx.table.shape[0], ptr(g_arena.contiguous()), None, stream()),
+                      'pack_arena_backward')
             return (None, None, None, None) + (None,) * len(tensors)
         flat = torch.empty(ctx.n_grad, device=g_arena.device, dtype=torch.float32)
-        check(_lib.lib().mb_pack_arena_backward(ptr(ctx.table), ptr(ctx.gtable), ctx.table.shape[0], ptr(g_arena.contiguous()), ptr(flat),
-                                                stream()), 'pack_arena_backward')
+        with _lib.timed('pack_arena_bwd'):
+            check(_lib.lib().mb_pack_arena_backward(ptr(ctx.table), ptr(ctx.gtable), ctx.table.shape[0], ptr(g_arena.contiguous()), ptr(flat),
+                                                    stream()), 'pack_arena_backward')
         grads, off = [], 0
         for t in tensors:
             grads.append(flat[off:off + t.numel()].view(t.shape))

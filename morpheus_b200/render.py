@@ -27,8 +27,9 @@ class _RayPoints(torch.autograd.Function):
         rays_o, rays_d = rays_o.contiguous().float(), rays_d.contiguous().float()
         M = ray_indices.shape[0]
         xyz = torch.empty(M, 3, device=rays_o.device, dtype=torch.float32)
-        check(_lib.lib().mb_ray_points_forward(ptr(rays_o), ptr(rays_d), ptr(ray_indices), ptr(t_starts), ptr(t_ends), M, ptr(xyz), stream()),
-              'ray_points_forward')
+        with _lib.timed('ray_points_fwd'):
+            check(_lib.lib().mb_ray_points_forward(ptr(rays_o), ptr(rays_d), ptr(ray_indices), ptr(t_starts), ptr(t_ends), M, ptr(xyz), stream()),
+                  'ray_points_forward')
         ctx.save_for_backward(t_starts, t_ends, seg)
         ctx.n_rays = rays_o.shape[0]
         return xyz
@@ -40,8 +41,9 @@ class _RayPoints(torch.autograd.Function):
         g_o = torch.empty(N, 3, device=g_xyz.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
         g_d = torch.empty(N, 3, device=g_xyz.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
         if g_o is not None or g_d is not None:
-            check(_lib.lib().mb_ray_points_backward(ptr(seg), N, ptr(t_starts), ptr(t_ends), ptr(g_xyz.contiguous().float()), ptr(g_o), ptr(g_d),
-                                                    stream()), 'ray_points_backward')
+            with _lib.timed('ray_points_bwd'):
+                check(_lib.lib().mb_ray_points_backward(ptr(seg), N, ptr(t_starts), ptr(t_ends), ptr(g_xyz.contiguous().float()), ptr(g_o), ptr(g_d),
+                                                        stream()), 'ray_points_backward')
         return g_o, g_d, None, None, None, None
 
 
@@ -52,8 +54,9 @@ class _SdfLoss(torch.autograd.Function):
     def forward(ctx, sdf, t_starts, t_ends, ray_indices, depth, mask, trunc):
         sdf = sdf.contiguous().float()
         out = torch.zeros(2, device=sdf.device, dtype=torch.float32)
-        check(_lib.lib().mb_sdf_loss_forward(ptr(t_starts), ptr(t_ends), ptr(ray_indices), ptr(depth), ptr(mask), ptr(sdf), sdf.shape[0],
-                                             _lib.C.c_float(trunc), ptr(out), stream()), 'sdf_loss_forward')
+        with _lib.timed('sdf_loss_fwd'):
+            check(_lib.lib().mb_sdf_loss_forward(ptr(t_starts), ptr(t_ends), ptr(ray_indices), ptr(depth), ptr(mask), ptr(sdf), sdf.shape[0],
+                                                 _lib.C.c_float(trunc), ptr(out), stream()), 'sdf_loss_forward')
         ctx.save_for_backward(sdf, t_starts, t_ends, ray_indices, depth, mask)
         ctx.trunc = trunc
         return out
@@ -62,8 +65,9 @@ class _SdfLoss(torch.autograd.Function):
     def backward(ctx, g_out):
         sdf, t_starts, t_ends, ray_indices, depth, mask = ctx.saved_tensors
         g_sdf = torch.empty_like(sdf)
-        check(_lib.lib().mb_sdf_loss_backward(ptr(t_starts), ptr(t_ends), ptr(ray_indices), ptr(depth), ptr(mask), ptr(sdf), sdf.shape[0],
-                                              _lib.C.c_float(ctx.trunc), ptr(g_out.contiguous().float()), ptr(g_sdf), stream()), 'sdf_loss_backward')
+        with _lib.timed('sdf_loss_bwd'):
+            check(_lib.lib().mb_sdf_loss_backward(ptr(t_starts), ptr(t_ends), ptr(ray_indices), ptr(depth), ptr(mask), ptr(sdf), sdf.shape[0],
+                                                  _lib.C.c_float(ctx.trunc), ptr(g_out.contiguous().float()), ptr(g_sdf), stream()), 'sdf_loss_backward')
         return g_sdf, None, None, None, None, None, None
 
 

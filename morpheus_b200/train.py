@@ -47,10 +47,11 @@ class _RayLoss(torch.autograd.Function):
         N = opacity.shape[0]
         out = torch.zeros(1, device=image.device, dtype=torch.float32)
         g_i, g_o, g_d = torch.empty_like(image), torch.empty_like(opacity), torch.empty_like(depth)
-        check(_lib.lib().mb_ray_loss(ptr(image), ptr(opacity), ptr(depth), ptr(gt_rgb.contiguous().float()), ptr(gt_depth.contiguous().float()),
-                                     ptr(gt_mask.contiguous().float()), ptr(rays_o.contiguous().float()), ptr(rays_d.contiguous().float()), N,
-                                     C.c_float(w_rgb), C.c_float(w_mask), C.c_float(w_depth), ptr(out), ptr(g_i), ptr(g_o), ptr(g_d), stream()),
-              'ray_loss')
+        with _lib.timed('ray_loss'):
+            check(_lib.lib().mb_ray_loss(ptr(image), ptr(opacity), ptr(depth), ptr(gt_rgb.contiguous().float()), ptr(gt_depth.contiguous().float()),
+                                         ptr(gt_mask.contiguous().float()), ptr(rays_o.contiguous().float()), ptr(rays_d.contiguous().float()), N,
+                                         C.c_float(w_rgb), C.c_float(w_mask), C.c_float(w_depth), ptr(out), ptr(g_i), ptr(g_o), ptr(g_d), stream()),
+                  'ray_loss')
         ctx.save_for_backward(g_i, g_o, g_d)
         return out[0]
 
