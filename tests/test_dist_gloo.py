@@ -30,27 +30,31 @@ def _problem():
     return N, S, theta, ray_depth, z, feats, rgb_gt
 
 
-def _shard_loss(theta, lo, hi, world, N, S, ray_depth, z, feats, rgb_gt):
+def _shard_loss(theta, lo, hi, world, N, S, ray_depth, z, feats, rgb_gt, shipped=False):
     from morpheus_b200.render import get_sdf_loss, global_count
     ri = torch.arange(lo, hi).repeat_interleave(S)
     sl = slice(lo * S, hi * S)
     sdf = feats[sl] @ theta
     t_gt = ray_depth[ri][:, None]
-    cnt = global_count(torch.count_nonzero(t_gt), world) if world > 1 else None
+    if shipped and world > 1:
+        # bench.py / train.GraphedStep: whoever shards the batch ships the global count with the shard ('n_depth'), no collective
+        cnt = torch.count_nonzero(ray_depth).float() * S / world
+    else:
+        cnt = global_count(torch.count_nonzero(t_gt), world) if world > 1 else None
     _, sdf_loss = get_sdf_loss(z[sl], t_gt, sdf, 0.5, mask=torch.ones_like(t_gt), rays_w_depth=cnt)
     img = torch.sigmoid(sdf.view(hi - lo, S).mean(1, keepdim=True) * torch.ones(1, 3))
     rgb_loss = torch.nn.functional.mse_loss(img, rgb_gt[lo:hi])
     return 5.0 * rgb_loss + 10.0 * sdf_loss
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, shipped=False):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     N, S, theta, *rest = _problem()
     th = theta.clone().requires_grad_(True)
     n_local = N // world
-    loss = _shard_loss(th, rank * n_local, (rank + 1) * n_local, world, N, S, *rest)
+    loss = _shard_loss(th, rank * n_local, (rank + 1) * n_local, world, N, S, *rest, shipped=shipped)
     (loss / world).backward()
     flat = th.grad.clone()
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
@@ -60,14 +64,15 @@ def _worker(rank, world, port, q):
 
 
 @pytest.mark.timeout(120)
-def test_sharded_gradient_equals_single_process():
+@pytest.mark.parametrize('shipped', [False, True])
+def test_sharded_gradient_equals_single_process(shipped):
     N, S, theta, *rest = _problem()
     th = theta.clone().requires_grad_(True)
     _shard_loss(th, 0, N, 1, N, S, *rest).backward()
     ctx = mp.get_context('spawn')
     q = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, shipped)) for r in range(2)]
     for p in procs:
         p.start()
     got = q.get()
