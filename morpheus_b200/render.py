@@ -253,7 +253,8 @@ class Renderer:
             rays_mask = rays_mask.contiguous().view(-1, 1)
         N = rays_o.shape[0]
         results = {}
-        if samples is None and self.uniform_samples:
+        used_uniform = samples is None and bool(self.uniform_samples)      # exactly S samples per ray (the count shortcut below relies on it)
+        if used_uniform:
             samples = self.sample_uniform(rays_o, rays_d, self.uniform_samples, jitter)
         if samples is None:
             with torch.no_grad():
@@ -308,7 +309,7 @@ class Renderer:
             if rays_depth is not None:
                 if self.sdf_count_override is not None:
                     cnt = self.sdf_count_override
-                elif self.uniform_samples:
+                elif used_uniform:
                     cnt = torch.count_nonzero(rays_depth) * self.uniform_samples      # == count_nonzero(depth[ray_indices])
                     if self.world_size > 1:
                         cnt = global_count(cnt, self.world_size)
