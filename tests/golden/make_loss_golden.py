@@ -1,0 +1,38 @@
+"""Generate tests/golden/loss_sdf.npz by running the UNMODIFIED reference `utils.get_sdf_loss`
+(/root/reference/utils.py:91-113) on CPU with seeded inputs (values + autograd gradient w.r.t. the predicted SDF).
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_loss_golden.py
+One shim: `cv2` (imported at the top of the reference's utils.py, unused by get_sdf_loss) -> empty module.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+sys.modules.setdefault('cv2', types.ModuleType('cv2'))
+sys.path.insert(0, '/root/reference')
+import utils as ref_utils  # noqa: E402  (reference, unmodified)
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+g = torch.Generator().manual_seed(1234)
+cases = {}
+for name, M, with_mask in (('masked', 4000, True), ('nomask', 1500, False)):
+    z = torch.rand(M, 1, generator=g) * 3.0
+    d = torch.rand(M, 1, generator=g) * 2.5 + 0.2
+    d[::7] = 0.0                      # no depth observation
+    d[3::11] = -1.0                   # invalid depth marker (front-mask branch z < 3.5)
+    near = torch.arange(0, M, 5)
+    z[near] = d[near] + (torch.rand(near.shape[0], 1, generator=g) - 0.5) * 0.15      # samples inside / around the truncation band
+    mask = (torch.rand(M, 1, generator=g) > 0.3).float() if with_mask else None
+    sdf = (torch.randn(M, generator=g) * 0.2).requires_grad_(True)
+    fs, sl = ref_utils.get_sdf_loss(z, d, sdf, 0.1, mask=mask)
+    gfs, = torch.autograd.grad(fs, sdf, retain_graph=True)
+    gsl, = torch.autograd.grad(sl, sdf)
+    cases[name] = dict(z=z, d=d, sdf=sdf.detach(), fs=fs.detach(), sl=sl.detach(), gfs=gfs, gsl=gsl)
+    if mask is not None:
+        cases[name]['mask'] = mask
+np.savez_compressed(os.path.join(OUT, 'loss_sdf.npz'), **{f'{c}_{k}': v.numpy() for c, vs in cases.items() for k, v in vs.items()})
+print({c: (float(v['fs']), float(v['sl'])) for c, v in cases.items()})

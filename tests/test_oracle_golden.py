@@ -78,3 +78,26 @@ def test_gradients(golden_dir, tag):
                  'color_net.net.1.weight_v', 'color_net.net.1.weight_g', 'deform_net.net.0.weight_v', 'deform_net.net.5.weight_g',
                  'topo_net.net.3.weight_v', 'deform_code.volumes.0', 'deform_code.volumes.2', 'sdf2density.beta'):
         assert relerr(sd[name].grad.numpy(), z['grad.' + name]) < 2e-3, name
+
+
+@pytest.mark.parametrize('case', ['masked', 'nomask'])
+def test_sdf_loss_restatements_vs_reference_golden(case):
+    """utils.get_sdf_loss (utils.py:91-113): the oracle restatement (oracle/render.py) and the product's torch form
+    (morpheus_b200.render.get_sdf_loss, which the GPU test pins the mb_sdf_loss_* kernels to) against values and gradients
+    produced by the UNMODIFIED reference function (tests/golden/make_loss_golden.py)."""
+    import numpy as np
+    import torch
+    from morpheus_b200 import render as mr
+    from oracle import render as orr
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'loss_sdf.npz'))
+    get = lambda k: torch.from_numpy(z[f'{case}_{k}'])      # noqa: E731
+    mask = get('mask') if f'{case}_mask' in z.files else None
+    for fn in (orr.get_sdf_loss, mr.get_sdf_loss):
+        sdf = get('sdf').clone().requires_grad_(True)
+        fs, sl = fn(get('z'), get('d'), sdf, 0.1, mask=mask)
+        assert abs(float(fs) - float(get('fs'))) <= 1e-6 * max(1.0, abs(float(get('fs'))))
+        assert abs(float(sl) - float(get('sl'))) <= 1e-6 * max(1.0, abs(float(get('sl'))))
+        gfs, = torch.autograd.grad(fs, sdf, retain_graph=True)
+        gsl, = torch.autograd.grad(sl, sdf)
+        assert torch.allclose(gfs, get('gfs'), rtol=1e-5, atol=1e-9)
+        assert torch.allclose(gsl, get('gsl'), rtol=1e-5, atol=1e-9)
