@@ -36,3 +36,15 @@ for name, M, with_mask in (('masked', 4000, True), ('nomask', 1500, False)):
         cases[name]['mask'] = mask
 np.savez_compressed(os.path.join(OUT, 'loss_sdf.npz'), **{f'{c}_{k}': v.numpy() for c, vs in cases.items() for k, v in vs.items()})
 print({c: (float(v['fs']), float(v['sl'])) for c, v in cases.items()})
+
+# ---- pinhole ray directions: datasets/utils.py:28-65 (get_camera_rays, OpenGL convention, un-normalised) ----
+import importlib.util  # noqa: E402
+spec = importlib.util.spec_from_file_location('ref_dataset_utils', '/root/reference/datasets/utils.py')
+ref_du = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(ref_du)
+H, W = 9, 12
+dirs = ref_du.get_camera_rays(H, W, torch.tensor(517.0 / 30), torch.tensor(500.0 / 30), 6.3, 4.1)
+dirs_default = ref_du.get_camera_rays(H, W, torch.tensor(20.0))
+np.savez_compressed(os.path.join(OUT, 'camera_rays.npz'), dirs=dirs.numpy(), dirs_default=dirs_default.numpy(),
+                    H=H, W=W, fx=517.0 / 30, fy=500.0 / 30, cx=6.3, cy=4.1)
+print('camera rays', tuple(dirs.shape))

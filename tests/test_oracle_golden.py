@@ -101,3 +101,18 @@ def test_sdf_loss_restatements_vs_reference_golden(case):
         gsl, = torch.autograd.grad(sl, sdf)
         assert torch.allclose(gfs, get('gfs'), rtol=1e-5, atol=1e-9)
         assert torch.allclose(gsl, get('gsl'), rtol=1e-5, atol=1e-9)
+
+
+def test_camera_rays_vs_reference_golden():
+    """datasets/utils.py:28-65 get_camera_rays (OpenGL, un-normalised): product (morpheus_b200.render.get_camera_rays) and oracle
+    (oracle.render.camera_dirs) against the unmodified reference function's output."""
+    import numpy as np
+    import torch
+    from morpheus_b200 import render as mr
+    from oracle import render as orr
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'camera_rays.npz'))
+    H, W = int(z['H']), int(z['W'])
+    ours = mr.get_camera_rays(H, W, float(z['fx']), float(z['fy']), float(z['cx']), float(z['cy']), device='cpu')
+    assert torch.equal(ours, torch.from_numpy(z['dirs']))
+    assert torch.equal(orr.camera_dirs(H, W, float(z['fx']), float(z['fy']), float(z['cx']), float(z['cy'])), torch.from_numpy(z['dirs']))
+    assert torch.equal(mr.get_camera_rays(H, W, 20.0, device='cpu'), torch.from_numpy(z['dirs_default']))
