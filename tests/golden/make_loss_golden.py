@@ -48,3 +48,17 @@ dirs_default = ref_du.get_camera_rays(H, W, torch.tensor(20.0))
 np.savez_compressed(os.path.join(OUT, 'camera_rays.npz'), dirs=dirs.numpy(), dirs_default=dirs_default.numpy(),
                     H=H, W=W, fx=517.0 / 30, fy=500.0 / 30, cx=6.3, cy=4.1)
 print('camera rays', tuple(dirs.shape))
+
+# ---- look-at poses of the virtual views: datasets/dataset.py:225-266 (get_c2w_from_cam_center, OpenGL, keep_chirality) ----
+pkg = types.ModuleType('ref_datasets')      # the reference package is called `datasets` (clashes with the HuggingFace package): load it under an alias
+pkg.__path__ = ['/root/reference/datasets']
+sys.modules['ref_datasets'] = pkg
+import importlib  # noqa: E402
+ref_ds = importlib.import_module('ref_datasets.dataset')  # (reference, unmodified; cv2 stubbed above)
+g2 = torch.Generator().manual_seed(77)
+centers = torch.randn(16, 3, generator=g2) * 2.0
+centers[0] = torch.tensor([0.0, 0.0, 2.5])
+centers[1] = torch.tensor([2.5, 0.3, 0.0])
+poses = ref_ds.DeformDataset.get_c2w_from_cam_center(None, centers, targets=0, camera_convention='OpenGL')
+np.savez_compressed(os.path.join(OUT, 'lookat_poses.npz'), centers=centers.numpy(), poses=poses.numpy())
+print('poses', tuple(poses.shape))

@@ -116,3 +116,14 @@ def test_camera_rays_vs_reference_golden():
     assert torch.equal(ours, torch.from_numpy(z['dirs']))
     assert torch.equal(orr.camera_dirs(H, W, float(z['fx']), float(z['fy']), float(z['cx']), float(z['cy'])), torch.from_numpy(z['dirs']))
     assert torch.equal(mr.get_camera_rays(H, W, 20.0, device='cpu'), torch.from_numpy(z['dirs_default']))
+
+
+def test_lookat_poses_vs_reference_golden():
+    """datasets/dataset.py:225-266 get_c2w_from_cam_center (OpenGL, keep_chirality): morpheus_b200.rays.c2w_from_cam_center against
+    the unmodified reference method's output."""
+    import numpy as np
+    import torch
+    from morpheus_b200 import rays
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'lookat_poses.npz'))
+    ours = rays.c2w_from_cam_center(torch.from_numpy(z['centers']), 0.0)
+    assert torch.allclose(ours, torch.from_numpy(z['poses']), rtol=0, atol=1e-7)
