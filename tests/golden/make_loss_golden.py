@@ -62,3 +62,18 @@ centers[1] = torch.tensor([2.5, 0.3, 0.0])
 poses = ref_ds.DeformDataset.get_c2w_from_cam_center(None, centers, targets=0, camera_convention='OpenGL')
 np.savez_compressed(os.path.join(OUT, 'lookat_poses.npz'), centers=centers.numpy(), poses=poses.numpy())
 print('poses', tuple(poses.shape))
+
+# ---- SDS view-angle weighting: models/guidance/zero123_utils.py:102-120 (angle_between), executed from the reference source text
+#      (the module itself imports diffusers / omegaconf / ldm, absent offline) ----
+import ast  # noqa: E402
+src = open('/root/reference/models/guidance/zero123_utils.py').read()
+fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == 'angle_between')
+ns = {'torch': torch, 'np': np}
+exec(compile(ast.Module(body=[fn], type_ignores=[]), 'zero123_utils.angle_between', 'exec'), ns)
+g3 = torch.Generator().manual_seed(5)
+v1 = torch.stack([2.5 + torch.rand(6, generator=g3) * 0.4, torch.deg2rad(90 + (torch.rand(6, generator=g3) - 0.5) * 90),
+                  torch.deg2rad((torch.rand(6, generator=g3) - 0.5) * 360)], -1)
+v2 = torch.tensor([[2.5, np.deg2rad(90.0), 0.0], [2.5, np.deg2rad(80.0), np.deg2rad(120.0)]], dtype=torch.float32)
+angles = ns['angle_between'](None, v1, v2)
+np.savez_compressed(os.path.join(OUT, 'sds_angles.npz'), v1=v1.numpy(), v2=v2.numpy(), angles=angles.numpy())
+print('angles', tuple(angles.shape))

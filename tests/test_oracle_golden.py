@@ -127,3 +127,16 @@ def test_lookat_poses_vs_reference_golden():
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'lookat_poses.npz'))
     ours = rays.c2w_from_cam_center(torch.from_numpy(z['centers']), 0.0)
     assert torch.allclose(ours, torch.from_numpy(z['poses']), rtol=0, atol=1e-7)
+
+
+def test_sds_view_angles_vs_reference_golden():
+    """zero123_utils.py:102-120 angle_between (drives the SDS grad_scale, :123-134): product (guidance.Zero123.angle_between, radians)
+    and oracle (oracle.sds.angle_between_deg) against the reference function's output."""
+    import numpy as np
+    import torch
+    from morpheus_b200 import guidance
+    from oracle import sds as osds
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'sds_angles.npz'))
+    v1, v2, ref = torch.from_numpy(z['v1']), torch.from_numpy(z['v2']), torch.from_numpy(z['angles'])
+    assert torch.allclose(guidance.Zero123.angle_between(v1, v2), ref, rtol=0, atol=2e-6)
+    assert torch.allclose(osds.angle_between_deg(v1, v2), torch.rad2deg(ref), rtol=0, atol=2e-4)
