@@ -77,3 +77,54 @@ v2 = torch.tensor([[2.5, np.deg2rad(90.0), 0.0], [2.5, np.deg2rad(80.0), np.deg2
 angles = ns['angle_between'](None, v1, v2)
 np.savez_compressed(os.path.join(OUT, 'sds_angles.npz'), v1=v1.numpy(), v2=v2.numpy(), angles=angles.numpy())
 print('angles', tuple(angles.shape))
+
+# ---- trainer-side pieces of morpheus.py, executed from the reference source text (the module imports nerfacc / the Zero-1-to-3
+#      stack, absent offline): get_real_view_render_loss (:946-983), get_ortho_normal_dir (:518-528), update_learning_rate (:471-502) ----
+import torch.nn.functional as F  # noqa: E402
+msrc = open('/root/reference/morpheus.py').read()
+mtree = ast.parse(msrc)
+
+
+def ref_method(name):
+    f = next(n for n in ast.walk(mtree) if isinstance(n, ast.FunctionDef) and n.name == name)
+    env = {'torch': torch, 'np': np, 'F': F, 'print': lambda *a, **k: None}
+    exec(compile(ast.Module(body=[f], type_ignores=[]), f'morpheus.{name}', 'exec'), env)
+    return env[name]
+
+
+cfg_train = {'rgb_weight': 5.0, 'mask_weight': 0.5, 'depth_weight': 0.1, 'warm_up_end': 200, 'n_epochs': 2000, 'lr': 5e-4}
+fake = types.SimpleNamespace(config={'train': cfg_train})
+g4 = torch.Generator().manual_seed(99)
+N = 301
+pred_rgb = torch.rand(N, 3, generator=g4).requires_grad_(True)
+pred_depth = (torch.rand(N, 1, generator=g4) * 3).requires_grad_(True)
+pred_mask = torch.rand(N, 1, generator=g4)
+pred_mask[:4] = 0.0
+pred_mask[4:8] = 1.0
+pred_mask.requires_grad_(True)
+gt_rgb = torch.rand(N, 3, generator=g4)
+gt_depth = torch.rand(N, generator=g4) * 2
+gt_depth[::5] = 0.0
+gt_mask = (torch.rand(N, generator=g4) > 0.4).float()
+rays_o = torch.randn(1, N, 3, generator=g4) * 0.3
+rays_d = torch.randn(1, N, 3, generator=g4) * 0.3
+# shapes as the trainer passes them for a real view (B = 1, H = N rays, W = 1; morpheus.py:915-944)
+loss = ref_method('get_real_view_render_loss')(fake, pred_rgb.t().reshape(1, 3, N, 1), pred_depth.reshape(1, 1, N, 1), pred_mask.reshape(1, 1, N, 1),
+                                               gt_rgb.t().reshape(1, 3, N, 1), gt_depth.reshape(1, N, 1), gt_mask.reshape(1, N, 1), rays_o, rays_d)
+grads = torch.autograd.grad(loss, [pred_rgb, pred_depth, pred_mask])
+torch.manual_seed(7)
+normals = torch.randn(50, 3, generator=g4)
+normals[0] = torch.tensor([0.0, 0.0, 1.0])
+wdir = ref_method('get_ortho_normal_dir')(fake, normals)
+lrs = {}
+for epoch in (0, 99, 100, 150, 199, 200, 1100, 2000):
+    groups = [{'name': n, 'lr': -1.0} for n in ('encoder_sdf', 'encoder_color', 'decoder_sdf', 'density', 'code_deform', 'pose')]
+    fk = types.SimpleNamespace(config={'train': cfg_train}, epoch=epoch, optimizer=types.SimpleNamespace(param_groups=groups))
+    ref_method('update_learning_rate')(fk)
+    lrs[epoch] = [g['lr'] for g in groups]
+np.savez_compressed(os.path.join(OUT, 'trainer_pieces.npz'), pred_rgb=pred_rgb.detach().numpy(), pred_depth=pred_depth.detach().numpy(),
+                    pred_mask=pred_mask.detach().numpy(), gt_rgb=gt_rgb.numpy(), gt_depth=gt_depth.numpy(), gt_mask=gt_mask.numpy(),
+                    rays_o=rays_o.numpy(), rays_d=rays_d.numpy(), loss=loss.detach().numpy(), g_rgb=grads[0].numpy(), g_depth=grads[1].numpy(),
+                    g_mask=grads[2].numpy(), normals=normals.numpy(), wdir=wdir.numpy(),
+                    lr_epochs=np.array(sorted(lrs)), lr_values=np.array([lrs[e] for e in sorted(lrs)]))
+print('trainer pieces: loss', float(loss))

@@ -140,3 +140,39 @@ def test_sds_view_angles_vs_reference_golden():
     v1, v2, ref = torch.from_numpy(z['v1']), torch.from_numpy(z['v2']), torch.from_numpy(z['angles'])
     assert torch.allclose(guidance.Zero123.angle_between(v1, v2), ref, rtol=0, atol=2e-6)
     assert torch.allclose(osds.angle_between_deg(v1, v2), torch.rad2deg(ref), rtol=0, atol=2e-4)
+
+
+def test_trainer_pieces_vs_reference_golden():
+    """Pieces of the reference trainer executed from its own source text (tests/golden/make_loss_golden.py):
+    get_real_view_render_loss (morpheus.py:946-983) vs train.real_view_loss_torch (the eager form the fused mb_ray_loss kernel is
+    pinned to on the GPU), get_ortho_normal_dir (:518-528) vs Renderer.get_ortho_normal_dir, update_learning_rate (:471-502) vs
+    train.learning_factor."""
+    import types
+    import numpy as np
+    import torch
+    from morpheus_b200 import train as mtrain
+    from morpheus_b200.render import Renderer
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'trainer_pieces.npz'))
+    t = lambda k: torch.from_numpy(z[k])      # noqa: E731
+    # ---- render loss heads ----
+    img, dep, opa = t('pred_rgb').clone().requires_grad_(True), t('pred_depth').clone().requires_grad_(True), t('pred_mask').clone().requires_grad_(True)
+    out = {'image': img, 'depth': dep.reshape(-1), 'weights_sum': opa}
+    batch = {'rgb': t('gt_rgb'), 'depth': t('gt_depth'), 'mask': t('gt_mask'), 'rays_o': t('rays_o').reshape(-1, 3), 'rays_d': t('rays_d').reshape(-1, 3)}
+    tr = dict(mtrain.DEFAULT_TRAIN_CFG, beta_weight=0.0)
+    model = types.SimpleNamespace(sdf2density=types.SimpleNamespace(get_beta=lambda: torch.zeros(())))
+    loss = mtrain.real_view_loss_torch(out, batch, model, tr)
+    assert abs(float(loss) - float(z['loss'])) < 1e-6 * max(1.0, abs(float(z['loss'])))
+    g = torch.autograd.grad(loss, [img, dep, opa])
+    assert torch.allclose(g[0], t('g_rgb'), rtol=1e-5, atol=1e-9)
+    assert torch.allclose(g[1].reshape(-1), t('g_depth').reshape(-1), rtol=1e-5, atol=1e-9)
+    assert torch.allclose(g[2].reshape(-1), t('g_mask').reshape(-1), rtol=1e-5, atol=1e-7)
+    # ---- random tangent direction: same draw (torch.manual_seed(7); rand(50, 1) * 2 pi) ----
+    torch.manual_seed(7)
+    phi = torch.rand(50, 1) * 2.0 * np.pi
+    w = Renderer.get_ortho_normal_dir(t('normals'), phi)
+    assert torch.allclose(w, t('wdir'), rtol=0, atol=1e-6)
+    # ---- learning-rate schedule: groups (encoder_sdf, encoder_color, decoder_sdf, density, code_deform, pose) ----
+    for epoch, lrs in zip(z['lr_epochs'], z['lr_values']):
+        lr = 5e-4 * mtrain.learning_factor(int(epoch), 200, 2000)
+        assert np.allclose(lrs[:5], lr, rtol=1e-12, atol=0)
+        assert np.isclose(lrs[5], lr * 0.1, rtol=1e-12, atol=0)
