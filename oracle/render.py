@@ -185,3 +185,28 @@ def render_rays(scene, rays_o, rays_d, rays_t, rays_id, samples, bg_color=None, 
                                   mask=rays_mask.reshape(-1, 1)[ray_indices] if rays_mask is not None else None)
             res['fs_loss'], res['sdf_loss'] = fs, sl
     return res
+
+
+# ------------------------------------------------------------------------------------------------
+# observation-space normal smoothness  (morpheus.py:518-556), RNG draws explicit
+# ------------------------------------------------------------------------------------------------
+def ortho_normal_dir(normals, phi):
+    """morpheus.py:518-528 with the random angle `phi` [.., 1] in [0, 2 pi) passed in"""
+    n = torch.nn.functional.normalize(normals, dim=-1)
+    u = torch.nn.functional.normalize(n[..., [1, 0, 2]] * torch.tensor([1., -1., 0.]), dim=-1)
+    v = torch.cross(n, u, dim=-1)
+    return torch.cos(phi) * u + torch.sin(phi) * v
+
+
+def normal_smoothness_loss(scene, rays_o, rays_d, rays_t, depth, trunc_noise, phi, trunc=0.1, smoothness_std=0.005):
+    """morpheus.py:530-556: 11 points per ray in a band around `depth`, normal(x, t) there and at a point displaced along a random
+    tangent, mean squared difference over the points inside the 1.1 sphere (boolean indexing, as the reference)."""
+    n_pts = int(trunc * 100 + 1)
+    tn = torch.linspace(-0.5 * trunc, 0.5 * trunc, n_pts) + 0.01 * trunc_noise
+    pts = ((depth.reshape(1, -1) + tn[:, None])[..., None] * rays_d[None, ...] + rays_o[None, ...]).view(-1, 3)
+    ts = rays_t[None, ...].repeat(n_pts, 1, 1).view(-1, 1)
+    keep = torch.linalg.norm(pts, ord=2, dim=-1) < 1.1
+    n1, _ = scene.normal(pts[keep], t=ts[keep])
+    w = ortho_normal_dir(n1, phi[keep] if phi.shape[0] == keep.shape[0] else phi)
+    n2, _ = scene.normal(pts[keep] + w * smoothness_std, t=ts[keep])
+    return torch.mean(torch.square(n1 - n2))

@@ -128,3 +128,26 @@ np.savez_compressed(os.path.join(OUT, 'trainer_pieces.npz'), pred_rgb=pred_rgb.d
                     g_mask=grads[2].numpy(), normals=normals.numpy(), wdir=wdir.numpy(),
                     lr_epochs=np.array(sorted(lrs)), lr_values=np.array([lrs[e] for e in sorted(lrs)]))
 print('trainer pieces: loss', float(loss))
+
+# ---- get_normal_smoothness_loss (morpheus.py:530-556) executed from the reference source, with the scene field provided by the
+#      oracle (oracle.fields.SceneOracle.normal; the field itself is pinned by tests/golden/scene_*.npz).  Inputs keep every band
+#      point inside the 1.1 sphere, so the reference's boolean indexing keeps all 11 N points and its two RNG draws
+#      (rand_like(trunc_normal), then rand([11 N, 1]) in get_ortho_normal_dir) can be replayed from the same seed. ----
+sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+from oracle.fields import SceneOracle, init_reference_like_state  # noqa: E402
+sd = init_reference_like_state(200, seed=21, randomize=True, emb_scale=0.3, sphere=True)
+scene = SceneOracle({k: v.clone() for k, v in sd.items()}, 1.01, 200, 1.0)
+g5 = torch.Generator().manual_seed(31)
+Nn = 10
+o5 = (torch.randn(Nn, 3, generator=g5) * 0.1).requires_grad_(True)
+d5 = torch.nn.functional.normalize(torch.randn(Nn, 3, generator=g5), dim=-1) * 0.4
+dep5 = (torch.rand(1, Nn, generator=g5) * 1.2 + 0.2).requires_grad_(True)
+t5 = torch.full((Nn, 1), 31.0 / 200)
+fake5 = types.SimpleNamespace(config={'train': {'trunc': 0.1, 'smoothness_std': 0.005}}, model=types.SimpleNamespace(normal=lambda x, t=None: scene.normal(x, t=t)))
+fake5.get_ortho_normal_dir = lambda normals: ref_method('get_ortho_normal_dir')(fake5, normals)
+torch.manual_seed(123)
+reg = ref_method('get_normal_smoothness_loss')(fake5, o5, d5, t5, dep5)
+g_o5, g_dep5 = torch.autograd.grad(reg, [o5, dep5])
+np.savez_compressed(os.path.join(OUT, 'normal_smoothness.npz'), rays_o=o5.detach().numpy(), rays_d=d5.numpy(), depth=dep5.detach().numpy(), t=t5.numpy(),
+                    loss=reg.detach().numpy(), g_o=g_o5.numpy(), g_depth=g_dep5.numpy(), seed=123)
+print('normal smoothness', float(reg))

@@ -176,3 +176,26 @@ def test_trainer_pieces_vs_reference_golden():
         lr = 5e-4 * mtrain.learning_factor(int(epoch), 200, 2000)
         assert np.allclose(lrs[:5], lr, rtol=1e-12, atol=0)
         assert np.isclose(lrs[5], lr * 0.1, rtol=1e-12, atol=0)
+
+
+def test_normal_smoothness_loss_vs_reference_golden():
+    """get_normal_smoothness_loss (morpheus.py:530-556) executed from the reference source (scene field = oracle) vs the oracle
+    restatement oracle.render.normal_smoothness_loss with the reference's two RNG draws replayed from the same seed; the product's
+    Renderer.get_normal_smoothness_loss is compared with the same formula on the GPU."""
+    import numpy as np
+    import torch
+    from oracle import render as orr
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'normal_smoothness.npz'))
+    sd = init_reference_like_state(200, seed=21, randomize=True, emb_scale=0.3, sphere=True)
+    scene = SceneOracle({k: v.clone() for k, v in sd.items()}, 1.01, 200, 1.0)
+    o = torch.from_numpy(z['rays_o']).clone().requires_grad_(True)
+    dep = torch.from_numpy(z['depth']).clone().requires_grad_(True)
+    N = o.shape[0]
+    torch.manual_seed(int(z['seed']))
+    trunc_noise = torch.rand(11)
+    phi = torch.rand(11 * N, 1) * 2.0 * np.pi
+    loss = orr.normal_smoothness_loss(scene, o, torch.from_numpy(z['rays_d']), torch.from_numpy(z['t']), dep, trunc_noise, phi)
+    assert abs(float(loss) - float(z['loss'])) < 1e-5 * abs(float(z['loss']))
+    g_o, g_dep = torch.autograd.grad(loss, [o, dep])
+    assert np.linalg.norm(g_o.numpy() - z['g_o']) < 1e-3 * np.linalg.norm(z['g_o'])
+    assert np.linalg.norm(g_dep.numpy() - z['g_depth']) < 1e-3 * np.linalg.norm(z['g_depth'])
