@@ -151,3 +151,59 @@ g_o5, g_dep5 = torch.autograd.grad(reg, [o5, dep5])
 np.savez_compressed(os.path.join(OUT, 'normal_smoothness.npz'), rays_o=o5.detach().numpy(), rays_d=d5.numpy(), depth=dep5.detach().numpy(), t=t5.numpy(),
                     loss=reg.detach().numpy(), g_o=g_o5.numpy(), g_depth=g_dep5.numpy(), seed=123)
 print('normal smoothness', float(reg))
+
+# ---- MorpheuS.render_rays (morpheus.py:558-794) executed from the reference source on the CPU.  Stand-ins: the scene field is the
+#      oracle (pinned by scene_*.npz), nerfacc's two compositing calls are the oracle restatements (nerfacc is not installable
+#      offline: that boundary stays unpinned), the sampler returns an injected fixed-S lattice; get_sdf_loss / safe_normalize are the
+#      reference's own.  This pins the GLUE of render_rays (ray points, light, blend, perturbed-normal loss, code regulariser, SDF
+#      loss wiring) that oracle.render.render_rays restates and every GPU render test checks the product against. ----
+from oracle import render as orr  # noqa: E402
+fake_nerfacc = types.SimpleNamespace(
+    render_weight_from_density=lambda t0, t1, sig, ray_indices=None, n_rays=None: orr.render_weight_from_density(t0, t1, sig, ray_indices, n_rays),
+    accumulate_along_rays=lambda w, values=None, ray_indices=None, n_rays=None: orr.accumulate_along_rays(w, values, ray_indices, n_rays))
+
+
+class _Model:
+    training = True
+
+    def __call__(self, x, t, light, ratio=1, shading='albedo', cano=False):
+        return scene.forward(x, t, light, ratio=ratio, shading=shading, cano=cano)
+
+    def normal(self, x, t=None, cano=False, topo=None):
+        return scene.normal(x, t=t, cano=cano, topo=topo)
+
+    def get_deform_code(self, t):
+        return scene.code(t)
+
+    def pose_optimisation(self, o, d, ids):
+        return scene.pose_optimisation(o, d, ids)
+
+
+fr = next(n for n in ast.walk(mtree) if isinstance(n, ast.FunctionDef) and n.name == 'render_rays')
+env = {'torch': torch, 'np': np, 'nerfacc': fake_nerfacc, 'safe_normalize': ref_du.safe_normalize, 'get_sdf_loss': ref_utils.get_sdf_loss}
+exec(compile(ast.Module(body=[fr], type_ignores=[]), 'morpheus.render_rays', 'exec'), env)
+g6 = torch.Generator().manual_seed(8)
+Nr, S = 24, 16
+c2w = orr.look_at_pose(70.0, 30.0, 2.5)
+dirs = orr.camera_dirs(360, 360, 517.0, 517.0, 180.0, 180.0).reshape(-1, 3)
+idx = torch.randint(0, dirs.shape[0], (Nr,), generator=g6)
+o6, d6 = orr.rays_from_pose(dirs[idx], c2w)
+aabb = torch.tensor([-1.01, -1.01, -1.01, 1.01, 1.01, 1.01])
+samples = orr.sample_uniform(o6, d6, aabb, S, torch.rand(Nr, generator=g6))
+t6 = torch.full((1, Nr, 1), 31.0 / 200)
+id6 = torch.full((1, Nr, 1), 31, dtype=torch.long)
+bg6 = torch.rand(Nr, 3, generator=g6)
+depth6 = torch.rand(Nr, generator=g6) * 1.5 + 1.5
+depth6[::4] = 0.0
+mask6 = (torch.rand(Nr, generator=g6) > 0.3).float()
+train_cfg = {'ori_weight': 0.01, 'normal_smooth_3d': 0.1, 'normal_dir': False, 'smoothness_std': 0.005, 'topo_none': True, 'normal_smooth_3d_t': 0.0,
+             'deform_smooth': 0.0, 'deform_smooth_t': 0.0, 'topo_smooth_t': 0.0, 'code_reg': 0.5, 'normal_smooth_2d': 0.0, 'normal_smoothness': 0.0, 'trunc': 0.1}
+fake6 = types.SimpleNamespace(config={'model': {'bg_radius': 1.4}, 'render': {'step_size': 0.01}, 'train': train_cfg}, model=_Model(),
+                              occupancy_grid=types.SimpleNamespace(sampling=lambda *a, **k: samples), dataset=types.SimpleNamespace(num_frames=200))
+torch.manual_seed(2024)
+res = env['render_rays'](fake6, o6[None], d6[None], t6, id6, Nr, 1, bg_color=bg6, ambient_ratio=1.0, shading='albedo_normal', real_view=True,
+                         rays_depth=depth6[None], rays_mask=mask6[None], optimize_pose=True)
+np.savez_compressed(os.path.join(OUT, 'render_rays_ref.npz'), rays_o=o6.numpy(), rays_d=d6.numpy(), ray_indices=samples[0].numpy(), t_starts=samples[1].numpy(),
+                    t_ends=samples[2].numpy(), bg=bg6.numpy(), depth_gt=depth6.numpy(), mask_gt=mask6.numpy(), seed=2024,
+                    **{k: v.detach().numpy() for k, v in res.items() if torch.is_tensor(v)})
+print('render_rays keys', sorted(k for k, v in res.items() if torch.is_tensor(v)))

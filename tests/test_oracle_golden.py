@@ -199,3 +199,49 @@ def test_normal_smoothness_loss_vs_reference_golden():
     g_o, g_dep = torch.autograd.grad(loss, [o, dep])
     assert np.linalg.norm(g_o.numpy() - z['g_o']) < 1e-3 * np.linalg.norm(z['g_o'])
     assert np.linalg.norm(g_dep.numpy() - z['g_depth']) < 1e-3 * np.linalg.norm(z['g_depth'])
+
+
+def test_render_rays_glue_vs_reference_source_golden():
+    """MorpheuS.render_rays (morpheus.py:558-794) executed from the reference source (stand-ins: oracle scene field, oracle
+    compositing, injected samples; tests/golden/make_loss_golden.py) vs oracle.render.render_rays -- the checker every GPU render
+    test and smoke() compare the product with -- with the reference's RNG draws (light offset, perturbation noise) replayed."""
+    import numpy as np
+    import torch
+    from oracle import render as orr
+    from oracle.fields import safe_normalize
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'render_rays_ref.npz'))
+    sd = init_reference_like_state(200, seed=21, randomize=True, emb_scale=0.3, sphere=True)
+    scene = SceneOracle({k: v.clone() for k, v in sd.items()}, 1.01, 200, 1.0)
+    t = lambda k: torch.from_numpy(z[k])      # noqa: E731
+    o, d = t('rays_o'), t('rays_d')
+    N = o.shape[0]
+    samples = (t('ray_indices'), t('t_starts'), t('t_ends'))
+    M = samples[0].shape[0]
+    rays_t = torch.full((1, N, 1), 31.0 / 200)
+    ids = torch.full((1, N, 1), 31, dtype=torch.long)
+    torch.manual_seed(int(z['seed']))
+    loff = torch.randn(3)
+    noise = torch.randn(M, 3)
+    with torch.no_grad():
+        o2, _ = scene.pose_optimisation(o, d, ids.view(-1, 1))
+        out = orr.render_rays(scene, o[None], d[None], rays_t, ids, samples, bg_color=t('bg'), ambient_ratio=1.0, light_d=safe_normalize(o2 + loff),
+                              shading='albedo_normal', optimize_pose=True, rays_depth=t('depth_gt')[None], rays_mask=t('mask_gt')[None],
+                              perturb_noise=noise, trunc=0.1, smoothness_std=0.005, training=True, real_view=True)
+        ts = rays_t.view(-1, 1)[:1]
+        loss_code = torch.square(2 * scene.code(ts) - scene.code(ts - 1 / 200) - scene.code(ts + 1 / 200)).mean()
+
+    def close(a, b, tol):
+        a, b = np.asarray(a, dtype=np.float64).reshape(-1), np.asarray(b, dtype=np.float64).reshape(-1)
+        return np.linalg.norm(a - b) <= tol * (np.linalg.norm(b) + 1e-12)
+    assert close(out['image'].numpy(), z['image'], 1e-6)
+    assert close(out['depth'].numpy(), z['depth'], 1e-6)
+    assert close(out['weights'].numpy(), z['weights'], 1e-6)
+    assert close(out['weights_sum'].numpy(), z['weights_sum'], 1e-6)
+    assert close(out['sdf'].numpy(), z['sdf'], 1e-6)
+    assert close(out['normal'].numpy(), z['normal'], 1e-5)
+    assert close(out['normal_raw'].numpy(), z['normal_raw'], 1e-5)
+    assert close(out['deform'].numpy(), z['deform'], 1e-6)
+    assert close(out['loss_normal_perturb'].numpy(), z['loss_normal_perturb'], 1e-5)
+    assert close(out['sdf_loss'].numpy(), z['sdf_loss'], 1e-6)
+    assert close(out['fs_loss'].numpy(), z['fs_loss'], 1e-6)
+    assert close(loss_code.numpy(), z['loss_code'], 1e-6)
