@@ -207,3 +207,47 @@ np.savez_compressed(os.path.join(OUT, 'render_rays_ref.npz'), rays_o=o6.numpy(),
                     t_ends=samples[2].numpy(), bg=bg6.numpy(), depth_gt=depth6.numpy(), mask_gt=mask6.numpy(), seed=2024,
                     **{k: v.detach().numpy() for k, v in res.items() if torch.is_tensor(v)})
 print('render_rays keys', sorted(k for k, v in res.items() if torch.is_tensor(v)))
+
+# ---- Zero123.train_step (models/guidance/zero123_utils.py:138-236) executed from the reference source with small deterministic
+#      stand-ins for the three networks (encode_imgs, cc_projection, apply_model: the real ones are pinned separately by
+#      sds_nets.npz against the reference UNetModel / Encoder classes) and the closed-form DDIM add_noise (diffusers is absent).
+#      Pins the SCALAR CHAIN the oracle (oracle/sds.py) restates: angle-based grad scale, pose token, CFG combination, per-view
+#      weights, w(t), nan_to_num, loss. ----
+from pathlib import Path  # noqa: E402
+ftrain = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == 'train_step')
+env2 = {'torch': torch, 'np': np, 'F': F, 'Path': Path, 'save_image': None}
+exec(compile(ast.Module(body=[ftrain], type_ignores=[]), 'zero123_utils.train_step', 'exec'), env2)
+
+
+def standin_encode(img256):                  # [1,3,256,256] in [0,1] -> [1,4,32,32]
+    p = F.avg_pool2d(img256 * 2 - 1, 8)
+    return 0.18215 * torch.cat([p, p.mean(1, keepdim=True)], 1)
+
+
+def standin_apply(x_in, t_in, cond):         # 'hybrid' conditioning: x_in [2,4,32,32], c_concat [2,4,32,32], c_crossattn [2,1,768]
+    cc, ca = cond['c_concat'][0], cond['c_crossattn'][0]
+    return torch.tanh(0.5 * x_in + 0.1 * cc + ca.mean(dim=(1, 2))[:, None, None, None] + 1e-3 * t_in[:, None, None, None].float())
+
+
+betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2
+ac = torch.cumprod(1.0 - betas, 0)
+g7 = torch.Generator().manual_seed(11)
+ccw, ccb = torch.randn(768, 772, generator=g7) * 0.02, torch.randn(768, generator=g7) * 0.01
+fake7 = types.SimpleNamespace(
+    device='cpu', alphas=ac, min_step=20, max_step=500,
+    angle_between=lambda a, b: ns['angle_between'](None, a, b),
+    encode_imgs=standin_encode,
+    scheduler=types.SimpleNamespace(add_noise=lambda z, e, t: (ac[t] ** 0.5).view(-1, 1, 1, 1) * z + ((1 - ac[t]) ** 0.5).view(-1, 1, 1, 1) * e),
+    model=types.SimpleNamespace(cc_projection=lambda x: F.linear(x, ccw, ccb), apply_model=standin_apply))
+emb = {'c_crossattn': [torch.randn(1, 1, 768, generator=g7)], 'c_concat': [torch.randn(1, 4, 32, 32, generator=g7)],
+       'ref_radii': [2.5], 'ref_polars': [90.0], 'ref_azimuths': [0.0], 'zero123_ws': [1]}
+pred = torch.rand(1, 3, 72, 72, generator=g7).requires_grad_(True)
+polar, azimuth, radius = torch.tensor([10.0]), torch.tensor([200.0]), torch.tensor([0.1])
+t7 = torch.tensor([260])
+noise7 = torch.randn(1, 4, 32, 32, generator=g7)
+loss7, t_out, gs7, _ = env2['train_step'](fake7, emb, pred, polar, azimuth.clone(), radius, guidance_scale=5, grad_scale=0.01, t=t7, noise=noise7)
+gpred, = torch.autograd.grad(loss7, pred)
+np.savez_compressed(os.path.join(OUT, 'sds_chain.npz'), ccw=ccw.numpy(), ccb=ccb.numpy(), c_crossattn=emb['c_crossattn'][0].numpy(), c_concat=emb['c_concat'][0].numpy(),
+                    pred=pred.detach().numpy(), polar=polar.numpy(), azimuth=azimuth.numpy(), radius=radius.numpy(), t=t7.numpy(), noise=noise7.numpy(),
+                    loss=loss7.detach().numpy(), grad_scale=gs7.numpy(), g_pred=gpred.numpy())
+print('sds chain: loss', float(loss7), 'grad_scale', float(gs7))

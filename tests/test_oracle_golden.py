@@ -245,3 +245,41 @@ def test_render_rays_glue_vs_reference_source_golden():
     assert close(out['sdf_loss'].numpy(), z['sdf_loss'], 1e-6)
     assert close(out['fs_loss'].numpy(), z['fs_loss'], 1e-6)
     assert close(loss_code.numpy(), z['loss_code'], 1e-6)
+
+
+def test_sds_scalar_chain_vs_reference_source_golden():
+    """Zero123.train_step (zero123_utils.py:138-236) executed from the reference source with small stand-in networks
+    (tests/golden/make_loss_golden.py) vs the oracle chain of oracle/sds.py assembled exactly as tests/test_sds_gpu.py assembles it
+    to check morpheus_b200.guidance.Zero123.train_step on the GPU: loss, grad_scale and d(loss)/d(pred_rgb)."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from oracle import sds as osds
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'sds_chain.npz'))
+    t_ = lambda k: torch.from_numpy(z[k])      # noqa: E731
+
+    def standin_encode(img256):
+        p = F.avg_pool2d(img256 * 2 - 1, 8)
+        return 0.18215 * torch.cat([p, p.mean(1, keepdim=True)], 1)
+
+    def standin_apply(x_in, t_in, cc, ca):
+        return torch.tanh(0.5 * x_in + 0.1 * cc + ca.mean(dim=(1, 2))[:, None, None, None] + 1e-3 * t_in[:, None, None, None].float())
+
+    ac = osds.alphas_cumprod()
+    pred = t_('pred').clone().requires_grad_(True)
+    polar, azimuth, radius, t, noise = t_('polar'), t_('azimuth'), t_('radius'), t_('t'), t_('noise')
+    lat = standin_encode(F.interpolate(pred, (256, 256), mode='bilinear', align_corners=False))
+    ang = osds.angle_between_deg(torch.stack([radius + 2.5, torch.deg2rad(polar + 90.0), torch.deg2rad(azimuth + 0.0)], -1),
+                                 torch.tensor([[2.5, np.deg2rad(90.0), 0.0]]))
+    grad_scale = (torch.exp(ang.min(dim=1)[0] / 180.0) - 1) * 0.01
+    with torch.no_grad():
+        T = osds.pose_token(polar, azimuth, radius)
+        clip = F.linear(torch.cat([t_('c_crossattn'), T], -1), t_('ccw'), t_('ccb'))
+        x_in = torch.cat([osds.add_noise(lat.detach(), noise, t, ac)] * 2)
+        eps = standin_apply(x_in, torch.cat([t, t]), torch.cat([torch.zeros(1, 4, 32, 32), t_('c_concat')]), torch.cat([torch.zeros_like(clip), clip]))
+        grad = osds.sds_grad(eps[0:1], eps[1:2], noise, t, ac, 5.0, grad_scale)
+    loss = osds.sds_loss(lat, grad)
+    assert abs(float(grad_scale) - float(z['grad_scale'])) < 1e-6 * abs(float(z['grad_scale']))
+    assert abs(float(loss) - float(z['loss'])) < 1e-5 * abs(float(z['loss']))
+    g, = torch.autograd.grad(loss, pred)
+    assert np.linalg.norm(g.numpy() - z['g_pred']) < 1e-5 * np.linalg.norm(z['g_pred'])
