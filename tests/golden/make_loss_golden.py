@@ -251,3 +251,39 @@ np.savez_compressed(os.path.join(OUT, 'sds_chain.npz'), ccw=ccw.numpy(), ccb=ccb
                     pred=pred.detach().numpy(), polar=polar.numpy(), azimuth=azimuth.numpy(), radius=radius.numpy(), t=t7.numpy(), noise=noise7.numpy(),
                     loss=loss7.detach().numpy(), grad_scale=gs7.numpy(), g_pred=gpred.numpy())
 print('sds chain: loss', float(loss7), 'grad_scale', float(gs7))
+
+# ---- the complete real-view loss of one iteration (morpheus.py:1202-1236): get_real_view_render_loss + get_real_view_point_loss
+#      (:985-1029) + get_regularization_loss (:1090-1145), executed from the reference source with the weights of the SHIPPED
+#      configs/snoopy.yaml and the oracle scene as `model.density`. ----
+import yaml  # noqa: E402
+ytrain = yaml.safe_load(open('/root/reference/configs/snoopy.yaml'))['train']
+g8 = torch.Generator().manual_seed(321)
+N8 = 37
+sc8 = scene
+o8 = torch.randn(1, N8, 3, generator=g8) * 0.15
+d8 = torch.nn.functional.normalize(torch.randn(1, N8, 3, generator=g8), dim=-1) * 0.5
+t8 = torch.full((1, N8, 1), 77.0 / 200)
+gd8 = torch.rand(N8, generator=g8) * 1.2 + 0.1
+gd8[::6] = 0.0
+gm8 = (torch.rand(N8, generator=g8) > 0.35).float()
+grgb8 = torch.rand(N8, 3, generator=g8)
+prgb8, pdep8, pmask8 = torch.rand(N8, 3, generator=g8), torch.rand(N8, generator=g8) * 2, torch.rand(N8, generator=g8)
+outs8 = {'sdf_loss': torch.rand((), generator=g8), 'fs_loss': torch.rand((), generator=g8), 'loss_normal_perturb': torch.rand((), generator=g8),
+         'loss_code': torch.rand((), generator=g8), 'normal_reg': torch.rand((), generator=g8), 'normal_raw': torch.randn(N8 * 4, 3, generator=g8),
+         'deform': torch.randn(N8 * 4, 3, generator=g8), 'weights': torch.rand(N8 * 4, generator=g8)}
+beta8 = torch.tensor(0.1).abs() + 1e-4
+fake8 = types.SimpleNamespace(config={'train': ytrain, 'exp': {'end_iter': 1}}, global_step=0,
+                              model=types.SimpleNamespace(density=lambda x, t=None: sc8.density(x, t=t), sdf2density=types.SimpleNamespace(get_beta=lambda: beta8)))
+with torch.no_grad():
+    l_render = ref_method('get_real_view_render_loss')(fake8, prgb8.t().reshape(1, 3, N8, 1), pdep8.reshape(1, 1, N8, 1), pmask8.reshape(1, 1, N8, 1),
+                                                       grgb8.t().reshape(1, 3, N8, 1), gd8.reshape(1, N8, 1), gm8.reshape(1, N8, 1), o8, d8)
+    l_point = ref_method('get_real_view_point_loss')(fake8, grgb8.t().reshape(1, 3, N8, 1), gd8.reshape(1, N8, 1), gm8.reshape(1, N8, 1), o8, d8, t8, outs8)
+    l_reg = ref_method('get_regularization_loss')(fake8, outs8, None, cano=False)
+total8 = l_render + l_point + l_reg
+np.savez_compressed(os.path.join(OUT, 'real_view_total_loss.npz'), rays_o=o8.numpy(), rays_d=d8.numpy(), rays_t=t8.numpy(), gt_depth=gd8.numpy(), gt_mask=gm8.numpy(),
+                    gt_rgb=grgb8.numpy(), pred_rgb=prgb8.numpy(), pred_depth=pdep8.numpy(), pred_mask=pmask8.numpy(), beta=beta8.numpy(),
+                    l_render=l_render.numpy(), l_point=l_point.numpy(), l_reg=l_reg.numpy(), total=total8.numpy(),
+                    weight_names=np.array(sorted(k for k, v in ytrain.items() if isinstance(v, (int, float)) and not isinstance(v, bool))),
+                    weight_values=np.array([float(ytrain[k]) for k in sorted(k for k, v in ytrain.items() if isinstance(v, (int, float)) and not isinstance(v, bool))]),
+                    **{'o_' + k: v.numpy() for k, v in outs8.items()})
+print('real-view total loss', float(total8), float(l_render), float(l_point), float(l_reg))

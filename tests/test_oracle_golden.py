@@ -283,3 +283,33 @@ def test_sds_scalar_chain_vs_reference_source_golden():
     assert abs(float(loss) - float(z['loss'])) < 1e-5 * abs(float(z['loss']))
     g, = torch.autograd.grad(loss, pred)
     assert np.linalg.norm(g.numpy() - z['g_pred']) < 1e-5 * np.linalg.norm(z['g_pred'])
+
+
+def test_real_view_total_loss_and_shipped_weights_vs_reference_source_golden():
+    """The complete real-view loss of one iteration -- get_real_view_render_loss + get_real_view_point_loss + get_regularization_loss
+    (morpheus.py:946-1029, 1090-1145) executed from the reference source with the weights of the shipped configs/snoopy.yaml --
+    vs the product's loss assembly (train.real_view_loss_torch with FULL_TRAIN_CFG; the scene field is the oracle on both sides).
+    Also pins every weight of train.FULL_TRAIN_CFG to the yaml."""
+    import types
+    import numpy as np
+    import torch
+    from morpheus_b200 import train as mtrain
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'real_view_total_loss.npz'))
+    t_ = lambda k: torch.from_numpy(z[k])      # noqa: E731
+    shipped = dict(zip([str(n) for n in z['weight_names']], [float(v) for v in z['weight_values']]))
+    tr = dict(mtrain.FULL_TRAIN_CFG)
+    for k in ('rgb_weight', 'mask_weight', 'depth_weight', 'sdf_weight', 'fs_weight', 'surf_sdf_weight', 'surf_color_weight', 'normal_smoothness',
+              'normal_smooth_3d', 'smoothness_std', 'code_reg', 'beta_weight', 'ori_weight', 'trunc', 'lr'):
+        assert abs(float(tr[k]) - shipped[k]) < 1e-12, k
+    for k in ('normal_smooth_3d_t', 'normal_smooth_2d', 'eik_weight', 'sdf_reg', 'entropy_weight', 'deform_weight', 'deform_smooth', 'deform_smooth_t', 'topo_smooth_t'):
+        assert shipped[k] == 0.0, f'{k} is active in the shipped config but not implemented'
+    sd = init_reference_like_state(200, seed=21, randomize=True, emb_scale=0.3, sphere=True)
+    scene = SceneOracle({k: v.clone() for k, v in sd.items()}, 1.01, 200, 1.0)
+    model = types.SimpleNamespace(density=lambda x, t=None: scene.density(x, t=t), sdf2density=types.SimpleNamespace(get_beta=lambda: t_('beta')))
+    out = {'image': t_('pred_rgb'), 'depth': t_('pred_depth'), 'weights_sum': t_('pred_mask'), 'sdf_loss': t_('o_sdf_loss'), 'fs_loss': t_('o_fs_loss'),
+           'loss_normal_perturb': t_('o_loss_normal_perturb'), 'loss_code': t_('o_loss_code'), 'normal_reg': t_('o_normal_reg')}
+    batch = {'rgb': t_('gt_rgb'), 'depth': t_('gt_depth'), 'mask': t_('gt_mask'), 'rays_o': t_('rays_o').reshape(-1, 3), 'rays_d': t_('rays_d').reshape(-1, 3),
+             'rays_t': t_('rays_t').reshape(-1, 1)}
+    with torch.no_grad():
+        total = mtrain.real_view_loss_torch(out, batch, model, tr)
+    assert abs(float(total) - float(z['total'])) < 2e-6 * abs(float(z['total'])), (float(total), float(z['total']))
