@@ -51,11 +51,14 @@ def world_rays(dirs_cam, c2w):
 
 
 def virtual_view_rays(frame, num_frames, H, W, focal, scale, theta_range=(45.0, 105.0), phi_range=(-180.0, 180.0), radius=2.5,
-                      ref_theta=90.0, ref_phi=0.0, ref_radius=2.5, generator=None, device='cpu'):
-    """get_virtual_view_rays (datasets/dataset.py:503-578) for one random training view."""
+                      ref_theta=90.0, ref_phi=0.0, ref_radius=2.5, generator=None, device='cpu', theta_deg=None, phi_deg=None):
+    """get_virtual_view_rays (datasets/dataset.py:503-578) for one random training view; the shipped configs use
+    uniform_sphere_rate 0 (configs/snoopy.yaml:18), i.e. polar / azimuth uniform in their ranges (get_virtual_view_data :467-470).
+    `theta_deg` / `phi_deg` inject the two draws (degrees; the reference wraps negative azimuths by +360 before use, :469)."""
     u = torch.rand(2, generator=generator)
-    theta = torch.tensor([theta_range[0] + float(u[0]) * (theta_range[1] - theta_range[0])])
-    phi = torch.tensor([phi_range[0] + float(u[1]) * (phi_range[1] - phi_range[0])])
+    theta = torch.tensor([theta_range[0] + float(u[0]) * (theta_range[1] - theta_range[0]) if theta_deg is None else float(theta_deg)])
+    phi = torch.tensor([phi_range[0] + float(u[1]) * (phi_range[1] - phi_range[0]) if phi_deg is None else float(phi_deg)])
+    phi[phi < 0] += 360.0
     pose = c2w_from_cam_center(cam_center_from_polar(theta, phi, torch.tensor([radius])))[0].to(device)
     h, w = int(scale * H), int(scale * W)
     dirs = get_camera_rays(h, w, focal * scale, focal * scale, 0.5 * W * scale, 0.5 * H * scale, device=device).reshape(-1, 3)

@@ -287,3 +287,24 @@ np.savez_compressed(os.path.join(OUT, 'real_view_total_loss.npz'), rays_o=o8.num
                     weight_values=np.array([float(ytrain[k]) for k in sorted(k for k, v in ytrain.items() if isinstance(v, (int, float)) and not isinstance(v, bool))]),
                     **{'o_' + k: v.numpy() for k, v in outs8.items()})
 print('real-view total loss', float(total8), float(l_render), float(l_point), float(l_reg))
+
+# ---- novel-view ray generation: DeformDataset.get_virtual_view_data / get_virtual_view_rays (datasets/dataset.py:435-578) called
+#      unbound on a stand-in dataset object carrying the shipped `data` config and the synthetic snoopy-shaped camera ----
+ycfg = yaml.safe_load(open('/root/reference/configs/snoopy.yaml'))
+DD = ref_ds.DeformDataset
+Fv = 200
+K = torch.eye(4)
+K[0, 0] = K[1, 1] = 517.0
+K[0, 2] = K[1, 2] = 180.0
+fake9 = types.SimpleNamespace(cfg=ycfg, num_frames=Fv, H=360, W=360, intrinsics=K, is_train=True, radius=torch.full((Fv,), 2.5),
+                              real_view_data={'theta': torch.full((Fv,), 90.0), 'phi': torch.zeros(Fv), 'radius': torch.full((Fv,), 2.5)})
+for name in ('get_radius', 'scale_intrinsics', 'get_c2w_from_cam_center', 'get_virtual_view_data'):
+    setattr(fake9, name, types.MethodType(getattr(DD, name), fake9))
+views = []
+for seed in (1, 2, 3):
+    torch.manual_seed(seed)
+    data = DD.get_virtual_view_rays(fake9, bs=1, t=12)
+    views.append(data)
+np.savez_compressed(os.path.join(OUT, 'virtual_views.npz'), n=len(views),
+                    **{f'v{i}_{k}': (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for i, dv in enumerate(views) for k, v in dv.items() if k != 'dir'})
+print('virtual views', [(float(v['polar']), float(v['azimuth'])) for v in views])

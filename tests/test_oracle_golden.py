@@ -313,3 +313,22 @@ def test_real_view_total_loss_and_shipped_weights_vs_reference_source_golden():
     with torch.no_grad():
         total = mtrain.real_view_loss_torch(out, batch, model, tr)
     assert abs(float(total) - float(z['total'])) < 2e-6 * abs(float(z['total'])), (float(total), float(z['total']))
+
+
+def test_virtual_view_rays_vs_reference_golden():
+    """DeformDataset.get_virtual_view_rays / get_virtual_view_data (datasets/dataset.py:435-578, shipped data config) vs
+    morpheus_b200.rays.virtual_view_rays with the two angle draws injected."""
+    import numpy as np
+    import torch
+    from morpheus_b200 import rays
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'virtual_views.npz'))
+    for i in range(int(z['n'])):
+        g = lambda k: z[f'v{i}_{k}']      # noqa: E731
+        v = rays.virtual_view_rays(frame=12, num_frames=200, H=360, W=360, focal=517.0, scale=0.2, theta_deg=float(g('polar')[0]) + 90.0,
+                                   phi_deg=float(g('azimuth')[0]))
+        assert (v['H'], v['W']) == (int(g('H')), int(g('W')))
+        assert np.allclose(v['rays_o'].numpy(), g('rays_o'), rtol=0, atol=2e-5)
+        assert np.allclose(v['rays_d'].numpy(), g('rays_d'), rtol=0, atol=2e-5)
+        assert np.allclose(v['rays_t'].numpy(), g('rays_t')) and np.array_equal(v['rays_id'].numpy(), g('rays_id'))
+        assert np.allclose(v['polar'].numpy(), g('polar'), atol=1e-4) and np.allclose(v['azimuth'].numpy(), g('azimuth'), atol=1e-4)
+        assert np.allclose(v['radius'].numpy(), g('radius'), atol=1e-6)
