@@ -96,3 +96,62 @@ def synthetic_real_view_batch(n_rays, seed, frame=41, num_frames=200, H=360, W=3
     batch = {'rays_o': o, 'rays_d': d, 'rays_t': torch.full((n_rays, 1), frame / num_frames),
              'rays_id': torch.full((n_rays, 1), frame, dtype=torch.long), 'rgb': rgb, 'depth': depth, 'mask': mask, 'bg': bg}
     return {k: v.to(device) for k, v in batch.items()}
+
+
+class RealViewData:
+    """Device-resident RGB-D sequence with the sampling interface of the reference dataset:
+    `get_real_view_rays` (datasets/dataset.py:336-396) + `sample_real_view_rays` (:398-433), known_view_scale 1.
+    The reference materialises the full [F, H*W, 3] origin / direction tables on the CPU once, gathers on the CPU every step and
+    copies the batch to the GPU (morpheus.py:841-850); here images / depths / masks / poses live on `device` and the rays of the
+    selected pixels are computed on the fly (2 small launches), so a step needs no host work and no H2D copy.
+
+    images [F,H,W,3] float, depths [F,H,W] float, masks [F,H,W], poses [F,4,4] (c2w, OpenGL), K [3,3] or [4,4]."""
+
+    def __init__(self, images, depths, masks, poses, K, device='cpu', theta=None, phi=None, radius=None):
+        self.device = torch.device(device)
+        self.num_frames, self.H, self.W = int(images.shape[0]), int(images.shape[1]), int(images.shape[2])
+        f32 = dict(device=self.device, dtype=torch.float32)
+        self.image = torch.as_tensor(images).to(**f32).permute(0, 3, 1, 2).contiguous()       # [F,3,H,W] as the reference keeps it
+        self.depth = torch.as_tensor(depths).to(**f32)
+        self.mask = torch.as_tensor(masks).to(device=self.device, dtype=torch.int64)
+        self.pose = torch.as_tensor(poses).to(**f32)
+        K = torch.as_tensor(K).to(**f32)
+        self.intri = K
+        self.dirs = get_camera_rays(self.H, self.W, K[0, 0], K[1, 1], K[0, 2], K[1, 2], device=self.device).reshape(-1, 3)
+        self.theta, self.phi, self.radius = theta, phi, radius
+
+    def sample_real_view_rays(self, idx=None, bs=1, ray_num=None, index=None, generator=None):
+        """same keys / shapes as the reference: rays_o / rays_d [bs, n, 3], rays_t [bs, n, 1], rays_id [bs, n, 1] int64, image
+        [bs, 3, n, 1], mask / depth [bs, n, 1], H = n, W = 1 (n = ray_num, or H*W when ray_num is None).  `idx` / `index` inject the
+        frame and pixel draws (torch.randint in the reference, :400,413)."""
+        if idx is None:
+            idx = torch.randint(0, self.num_frames, (bs,), generator=generator)
+        elif isinstance(idx, int):
+            idx = torch.tensor([idx])
+        idx = torch.as_tensor(idx).to(self.device).long()
+        bs = idx.shape[0]
+        if ray_num is not None and index is None:
+            index = torch.randint(0, self.H * self.W, (ray_num,), generator=generator)
+        full_frame = index is None
+        if full_frame:
+            index = torch.arange(self.H * self.W)
+        index = torch.as_tensor(index).to(self.device).long()
+        n = index.shape[0]
+        pose = self.pose[idx]                                                    # [bs,4,4]
+        d_cam = self.dirs[index]                                                 # [n,3]
+        rays_d = torch.sum(d_cam[None, :, None, :] * pose[:, None, :3, :3], -1)   # d_w = sum_j d_j R[:, j]
+        rays_o = pose[:, None, :3, 3].expand(bs, n, 3).contiguous()
+        out = {'rays_o': rays_o, 'rays_d': rays_d,
+               'rays_t': (idx.float() / self.num_frames)[:, None, None].expand(bs, n, 1).contiguous(),
+               'rays_id': idx[:, None, None].expand(bs, n, 1).contiguous(),
+               'image': self.image[idx].reshape(bs, 3, -1)[..., index].reshape(bs, 3, n, 1),
+               'mask': self.mask[idx].reshape(bs, -1)[..., index].reshape(bs, n, 1),
+               'depth': self.depth[idx].reshape(bs, -1)[..., index].reshape(bs, n, 1),
+               'H': n if not full_frame else self.H, 'W': 1 if not full_frame else self.W, 'intri': self.intri, 'pose': pose}
+        if full_frame:      # the reference leaves image / mask / depth of a whole frame in image layout (:402-411)
+            out['image'], out['mask'], out['depth'] = self.image[idx], self.mask[idx], self.depth[idx]
+        for k in ('theta', 'phi', 'radius'):
+            v = getattr(self, k)
+            if v is not None:
+                out[k] = torch.as_tensor(v).to(self.device)[idx]
+        return out

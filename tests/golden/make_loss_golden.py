@@ -308,3 +308,32 @@ for seed in (1, 2, 3):
 np.savez_compressed(os.path.join(OUT, 'virtual_views.npz'), n=len(views),
                     **{f'v{i}_{k}': (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for i, dv in enumerate(views) for k, v in dv.items() if k != 'dir'})
 print('virtual views', [(float(v['polar']), float(v['azimuth'])) for v in views])
+
+# ---- real-view ray tables + sampling: DeformDataset.get_real_view_rays / sample_real_view_rays (datasets/dataset.py:336-433) on a
+#      small synthetic RGB-D sequence (known_view_scale 1: cv2.resize to the same size is the identity, provided by the cv2 stub) ----
+sys.modules['cv2'].resize = lambda img, size, interpolation=None: img
+sys.modules['cv2'].INTER_LINEAR, sys.modules['cv2'].INTER_NEAREST = 1, 0
+g10 = torch.Generator().manual_seed(404)
+Fr, Hr, Wr = 5, 6, 8
+imgs = torch.rand(Fr, Hr, Wr, 3, generator=g10).numpy()
+deps = (torch.rand(Fr, Hr, Wr, generator=g10) * 3).numpy()
+msks = (torch.rand(Fr, Hr, Wr, generator=g10) > 0.5).numpy().astype(np.int64)
+cent = torch.randn(Fr, 3, generator=g10) * 2.0
+poses_r = DD.get_c2w_from_cam_center(None, cent, targets=0, camera_convention='OpenGL')
+Kr = torch.eye(4)
+Kr[0, 0], Kr[1, 1], Kr[0, 2], Kr[1, 2] = 11.5, 10.5, 4.2, 2.9
+fake10 = types.SimpleNamespace(cfg=ycfg, num_frames=Fr, H=Hr, W=Wr, intrinsics=Kr, poses=poses_r, images=imgs, depths=deps, masks=msks,
+                               theta=torch.rand(Fr, generator=g10), phi=torch.rand(Fr, generator=g10), radius=torch.rand(Fr, generator=g10))
+fake10.scale_intrinsics = types.MethodType(DD.scale_intrinsics, fake10)
+fake10.real_view_data = DD.get_real_view_rays(fake10)
+torch.manual_seed(9)
+smp = DD.sample_real_view_rays(fake10, ray_num=13)
+torch.manual_seed(9)
+idx_draw = torch.randint(0, Fr, (1,))
+index_draw = torch.randint(0, Hr * Wr, (13,))
+full = DD.sample_real_view_rays(fake10, idx=2)
+np.savez_compressed(os.path.join(OUT, 'real_view_rays.npz'), images=imgs, depths=deps, masks=msks, poses=poses_r.numpy(), K=Kr.numpy(),
+                    idx=idx_draw.numpy(), index=index_draw.numpy(),
+                    **{'s_' + k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in smp.items()},
+                    **{'f_' + k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in full.items() if k in ('rays_o', 'rays_d', 'rays_t', 'rays_id', 'image', 'depth', 'mask')})
+print('real-view rays', {k: tuple(v.shape) for k, v in smp.items() if torch.is_tensor(v)})

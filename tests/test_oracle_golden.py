@@ -332,3 +332,24 @@ def test_virtual_view_rays_vs_reference_golden():
         assert np.allclose(v['rays_t'].numpy(), g('rays_t')) and np.array_equal(v['rays_id'].numpy(), g('rays_id'))
         assert np.allclose(v['polar'].numpy(), g('polar'), atol=1e-4) and np.allclose(v['azimuth'].numpy(), g('azimuth'), atol=1e-4)
         assert np.allclose(v['radius'].numpy(), g('radius'), atol=1e-6)
+
+
+def test_real_view_sampling_vs_reference_golden():
+    """DeformDataset.get_real_view_rays + sample_real_view_rays (datasets/dataset.py:336-433) vs the device-resident
+    morpheus_b200.rays.RealViewData.sample_real_view_rays with the reference's two randint draws injected, and a full-frame fetch."""
+    import numpy as np
+    import torch
+    from morpheus_b200 import rays
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'real_view_rays.npz'))
+    data = rays.RealViewData(z['images'], z['depths'], z['masks'], z['poses'], z['K'])
+    s = data.sample_real_view_rays(idx=torch.from_numpy(z['idx']), ray_num=13, index=torch.from_numpy(z['index']))
+    assert (s['H'], s['W']) == (int(z['s_H']), int(z['s_W']))
+    for k in ('rays_o', 'rays_d', 'rays_t', 'image', 'depth'):
+        assert s[k].shape == z['s_' + k].shape and np.allclose(s[k].numpy(), z['s_' + k], rtol=0, atol=1e-6), k
+    for k in ('rays_id', 'mask'):
+        assert np.array_equal(s[k].numpy(), z['s_' + k]), k
+    f = data.sample_real_view_rays(idx=2)
+    for k in ('rays_o', 'rays_d', 'rays_t', 'image', 'depth'):
+        assert f[k].shape == z['f_' + k].shape and np.allclose(f[k].numpy(), z['f_' + k], rtol=0, atol=1e-6), k
+    for k in ('rays_id', 'mask'):
+        assert np.array_equal(f[k].numpy(), z['f_' + k]), k
