@@ -7,6 +7,7 @@ NCCL all-reduce of the flat gradient arena per step (the reference
 """
 import ctypes as C
 import math
+import random
 
 import torch
 import torch.distributed as dist
@@ -21,6 +22,7 @@ DEFAULT_TRAIN_CFG = {  # configs/snoopy.yaml:40-94 (only what the step reads)
     'beta_weight': 0.1, 'ori_weight': 0.01, 'trunc': 0.1, 'lr': 5e-4,
     # SURVEY 8f rank 1 (off in the BASELINE cfg-2 'mode B' step; FULL_TRAIN_CFG switches them on with the shipped weights)
     'normal_smoothness': 0.0, 'surf_sdf_weight': 0.0, 'surf_color_weight': 0.0,
+    'albedo_iter_ratio': 0.1, 'min_ambient_ratio': 0.1, 'textureless_ratio': 0.2, 'warm_up_end': 200, 'n_epochs': 2000, 'ema_decay': 0.95,
 }
 FULL_TRAIN_CFG = dict(DEFAULT_TRAIN_CFG, normal_smoothness=0.4, surf_sdf_weight=10.0, surf_color_weight=5.0)   # configs/snoopy.yaml:70-74
 
@@ -107,6 +109,40 @@ def real_view_loss_torch(out, batch, model, tr):
         loss = loss + surface_point_loss(model, batch, tr)
     loss = loss + tr['beta_weight'] * torch.mean(model.sdf2density.get_beta())
     return loss
+
+
+def progressive_level(exp_iter_ratio, enabled=True):
+    """morpheus.py:808-813: coarse-to-fine level of the hash grids / frequency bands, exp_iter_ratio = epoch / n_epochs"""
+    return min(1.0, 0.5 + 0.5 * exp_iter_ratio) if enabled else None
+
+
+def get_shading(exp_iter_ratio, real_view, tr, rng=random):
+    """morpheus.py:865-888 -> (ambient_ratio, shading).  Real views render 'albedo_normal' with ratio 1; virtual views use albedo
+    during the first `albedo_iter_ratio` of training, then a random ambient ratio and lambertian / textureless shading (same two
+    random.random() draws, in the same order, as the reference)."""
+    if real_view:
+        return 1.0, 'albedo_normal'
+    if exp_iter_ratio <= tr['albedo_iter_ratio']:
+        return 1.0, 'albedo'
+    ambient_ratio = tr['min_ambient_ratio'] + (1.0 - tr['min_ambient_ratio']) * rng.random()
+    shading = 'textureless' if rng.random() >= (1.0 - tr['textureless_ratio']) else 'lambertian'
+    return ambient_ratio, shading
+
+
+def get_bg_color(real_view, B, N, device, bg_radius=1.4, rng=random, generator=None):
+    """morpheus.py:890-903: per-ray random background on real views (also blended into the ground-truth image outside the mask,
+    :942); on virtual views None (= background network, only with cano) with probability 1/2, else one random colour"""
+    if real_view:
+        return torch.rand((B * N, 3), generator=generator).to(device)
+    if bg_radius > 0 and rng.random() > 0.5:
+        return None
+    return torch.rand(3, generator=generator).to(device)
+
+
+def blend_gt_background(gt_rgb, gt_mask, bg_color):
+    """get_gt_from_data, morpheus.py:939-942 on per-ray tensors: mask binarised at 0.5, gt = rgb * mask + bg * (1 - mask)"""
+    m = (gt_mask > 0.5).to(gt_rgb.dtype).reshape(-1, 1)
+    return gt_rgb * m + bg_color * (1 - m), m.reshape(-1)
 
 
 def learning_factor(epoch, warm_up_end, n_epochs, scale_factor=1.0):

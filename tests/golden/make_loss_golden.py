@@ -337,3 +337,37 @@ np.savez_compressed(os.path.join(OUT, 'real_view_rays.npz'), images=imgs, depths
                     **{'s_' + k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in smp.items()},
                     **{'f_' + k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in full.items() if k in ('rays_o', 'rays_d', 'rays_t', 'rays_id', 'image', 'depth', 'mask')})
 print('real-view rays', {k: tuple(v.shape) for k, v in smp.items() if torch.is_tensor(v)})
+
+# ---- per-iteration host choices: get_shading (morpheus.py:865-888), get_bg_color (:890-903), progressive_level (:808-813),
+#      get_gt_from_data blend (:929-944), executed from the reference source with the shipped weights; python / torch RNG seeded ----
+import random as pyrandom  # noqa: E402
+shade = []
+fake11 = types.SimpleNamespace(config={'train': ytrain, 'model': {'bg_radius': 1.4}}, device='cpu', model=types.SimpleNamespace(max_level=None))
+for m_name in ('get_shading', 'get_bg_color', 'progressive_level', 'get_gt_from_data'):
+    env_m = {'torch': torch, 'np': np, 'random': pyrandom}
+    f_m = next(n for n in ast.walk(mtree) if isinstance(n, ast.FunctionDef) and n.name == m_name)
+    exec(compile(ast.Module(body=[f_m], type_ignores=[]), f'morpheus.{m_name}', 'exec'), env_m)
+    setattr(fake11, m_name, types.MethodType(env_m[m_name], fake11))
+pyrandom.seed(5)
+for ratio in (0.0, 0.05, 0.1, 0.3, 0.6, 0.99):
+    for rv in (True, False):
+        a, sname = fake11.get_shading(ratio, rv)
+        shade.append((ratio, float(rv), a, {'albedo': 0, 'albedo_normal': 1, 'lambertian': 2, 'textureless': 3}[sname]))
+levels = []
+for ratio in (0.0, 0.25, 0.5, 1.0, 1.5):
+    fake11.progressive_level(ratio)
+    levels.append((ratio, fake11.model.max_level))
+pyrandom.seed(6)
+torch.manual_seed(6)
+bg_real = fake11.get_bg_color(True, B=1, N=9)
+bg_virtual = [fake11.get_bg_color(False) for _ in range(6)]
+g12 = torch.Generator().manual_seed(12)
+img12 = torch.rand(1, 3, 9, 1, generator=g12)
+dep12 = torch.rand(1, 9, 1, generator=g12)
+msk12 = torch.rand(1, 9, 1, generator=g12)
+gt_rgb12, gt_dep12, gt_msk12 = fake11.get_gt_from_data({'image': img12.clone(), 'depth': dep12.clone(), 'mask': msk12.clone()}, bg_real, 1, 9, 1)
+np.savez_compressed(os.path.join(OUT, 'host_choices.npz'), shade=np.array(shade), levels=np.array(levels), bg_real=bg_real.numpy(),
+                    bg_virtual_none=np.array([b is None for b in bg_virtual]), bg_virtual=np.stack([b.numpy() if b is not None else np.zeros(3, np.float32) for b in bg_virtual]),
+                    img=img12.numpy(), mask=msk12.numpy(), gt_rgb=gt_rgb12.numpy(), gt_mask=gt_msk12.numpy(),
+                    albedo_iter_ratio=ytrain['albedo_iter_ratio'], min_ambient_ratio=ytrain['min_ambient_ratio'], textureless_ratio=ytrain['textureless_ratio'])
+print('host choices', len(shade), levels[-1])

@@ -36,3 +36,36 @@ def test_flat_ema_matches_torch_ema_recurrence():
     assert torch.equal(flat, ema.shadow)
     ema.restore()
     assert torch.equal(flat, before)
+
+
+def test_per_iteration_host_choices_vs_reference_golden():
+    """get_shading / get_bg_color / progressive_level / the ground-truth background blend (morpheus.py:808-813, 865-903, 929-944)
+    executed from the reference source with seeded python / torch RNGs (tests/golden/make_loss_golden.py) vs the mirrors in
+    morpheus_b200.train driven by the same seeds."""
+    import os
+    import random
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'host_choices.npz'))
+    tr = dict(mtrain.DEFAULT_TRAIN_CFG)
+    for k in ('albedo_iter_ratio', 'min_ambient_ratio', 'textureless_ratio'):
+        assert abs(tr[k] - float(z[k])) < 1e-12
+    names = {0: 'albedo', 1: 'albedo_normal', 2: 'lambertian', 3: 'textureless'}
+    random.seed(5)
+    for ratio, rv, amb, sid in z['shade']:
+        a, s = mtrain.get_shading(float(ratio), bool(rv), tr)
+        assert s == names[int(sid)] and abs(a - float(amb)) < 1e-12
+    for ratio, lvl in z['levels']:
+        assert abs(mtrain.progressive_level(float(ratio)) - float(lvl)) < 1e-12
+    random.seed(6)
+    torch.manual_seed(6)
+    bg = mtrain.get_bg_color(True, 1, 9, 'cpu')
+    assert torch.equal(bg, torch.from_numpy(z['bg_real']))
+    for is_none, ref in zip(z['bg_virtual_none'], z['bg_virtual']):
+        b = mtrain.get_bg_color(False, None, None, 'cpu')
+        assert (b is None) == bool(is_none)
+        if b is not None:
+            assert torch.equal(b, torch.from_numpy(ref))
+    img = torch.from_numpy(z['img'])[0, :, :, 0].t()          # [N,3]
+    gt, m = mtrain.blend_gt_background(img, torch.from_numpy(z['mask']).reshape(-1), bg)
+    assert torch.allclose(gt, torch.from_numpy(z['gt_rgb'])[0, :, :, 0].t(), rtol=0, atol=1e-7)
+    assert torch.equal(m, torch.from_numpy(z['gt_mask']).reshape(-1))
