@@ -211,6 +211,14 @@ int mb_adam_step(float* p, const float* g, float* m, float* v, const uint8_t* gr
 int mb_adam_step_dev(float* p, const float* g, float* m, float* v, const uint8_t* group_id, const float* group_lr,
                      uint64_t n, float beta1, float beta2, float eps, const int32_t* step_dev, mb_stream_t stream);
 
+/* torch.optim.Adam's skip-if-grad-is-None semantics per parameter group: group_active [n_groups] u8 (0 = this step produced no gradient
+ * for the group: its p/m/v and its step count stay untouched), group_step [n_groups] i32 device counters (incremented here for the
+ * active groups; bias corrections use the group's own count, like torch's per-parameter `step`).  zero_after != 0 clears g after it
+ * was read (the next step's zero_grad() folded into this launch).  n_groups <= 32.  Graph-replayable. */
+int mb_adam_step_groups(float* p, float* g, float* m, float* v, const uint8_t* group_id, const float* group_lr,
+                        const uint8_t* group_active, int32_t* group_step, int n_groups, uint64_t n, float beta1, float beta2,
+                        float eps, int zero_after, mb_stream_t stream);
+
 /* ---- (7) SDS scalar chain: grad = grad_scale*(1-abar_t)*(eps_u + s*(eps_c-eps_u) - eps), nan_to_num --- */
 int mb_sds_grad(const float* eps_uncond, const float* eps_cond, const float* noise, float guidance_scale,
                 float w_t_times_grad_scale, float* grad, uint32_t n, mb_stream_t stream);

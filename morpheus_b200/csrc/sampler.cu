@@ -130,6 +130,47 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// Adam with torch.optim.Adam's PER-PARAMETER bookkeeping restated per group (morpheus.py:154-155 builds one Adam over the named groups of
+// models/model.py:313-324; on torch >= 2.0 zero_grad() sets .grad = None and Adam SKIPS such parameters: no moment decay, no step
+// increment, no move): group_active[g] == 0 -> the group's elements are left untouched; group_step[g] (incremented by the prologue
+// launch for active groups only) feeds the bias corrections.  zero_after != 0 folds the next step's zero_grad() into this launch.
+__global__ void adam_groups_prologue(int32_t* __restrict__ group_step, const uint8_t* __restrict__ group_active, int n_groups) {
+    const int g = threadIdx.x;
+    if (g < n_groups && group_active[g]) group_step[g] += 1;
+}
+__global__ void adam_groups_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                   const uint8_t* __restrict__ gid, const float* __restrict__ glr, const uint8_t* __restrict__ group_active,
+                                   const int32_t* __restrict__ group_step, int n_groups, uint64_t n, float b1, float b2, float eps, int zero_after) {
+    __shared__ float s_lr_bc1[32], s_bc2[32];
+    __shared__ uint8_t s_act[32];
+    if (threadIdx.x < 32) {
+        const int q = threadIdx.x;
+        float lr_bc1 = 0.f, bc2 = 1.f;
+        uint8_t a = 0;
+        if (q < n_groups) {
+            a = group_active[q];
+            const float t = (float)max(group_step[q], 1);
+            lr_bc1 = glr[q] / (1.0f - powf(b1, t));
+            bc2 = sqrtf(1.0f - powf(b2, t));
+        }
+        s_lr_bc1[q] = lr_bc1; s_bc2[q] = bc2; s_act[q] = a;
+    }
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int q = gid[i];
+        if (s_act[q]) {
+            const float gi = g[i];
+            const float mi = m[i] + (1.0f - b1) * (gi - m[i]);            // lerp form used by torch
+            const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+            m[i] = mi;
+            v[i] = vi;
+            const float denom = sqrtf(vi) / s_bc2[q] + eps;
+            p[i] = p[i] - s_lr_bc1[q] * (mi / denom);
+        }
+        if (zero_after) g[i] = 0.f;
+    }
+}
+
 // ---- SDS scalar chain (zero123_utils.py:177-212) -----------------------------------------------------
 __global__ void sds_grad_kernel(const float* __restrict__ eu, const float* __restrict__ ec, const float* __restrict__ noise,
                                 float s, float wg, float* __restrict__ grad, uint32_t n) {
@@ -221,6 +262,23 @@ extern "C" int mb_adam_step_dev(float* p, const float* g, float* m, float* v, co
     if (blocks > (uint64_t)sms * 8) blocks = (uint64_t)sms * 8;
     adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, group_id, group_lr, n, beta1, beta2, eps, 1.f, 1.f, step_dev);
     return check_launch("adam_step_dev");
+}
+
+extern "C" int mb_adam_step_groups(float* p, float* g, float* m, float* v, const uint8_t* group_id, const float* group_lr,
+                                   const uint8_t* group_active, int32_t* group_step, int n_groups, uint64_t n, float beta1, float beta2,
+                                   float eps, int zero_after, mb_stream_t stream) {
+    if (n == 0) return MB_OK;
+    if (!p || !g || !m || !v || !group_id || !group_lr || !group_active || !group_step || n_groups < 1 || n_groups > 32) {
+        set_error("adam_step_groups: bad argument (1 <= n_groups <= 32, no null pointers)");
+        return MB_EINVAL;
+    }
+    adam_groups_prologue<<<1, 32, 0, (cudaStream_t)stream>>>(group_step, group_active, n_groups);
+    int sms = mb_sm_count();
+    uint64_t blocks = (n + 255) / 256;
+    if (blocks > (uint64_t)sms * 8) blocks = (uint64_t)sms * 8;
+    adam_groups_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, group_id, group_lr, group_active, group_step, n_groups, n,
+                                                                          beta1, beta2, eps, zero_after);
+    return check_launch("adam_step_groups");
 }
 
 extern "C" int mb_sds_grad(const float* eps_uncond, const float* eps_cond, const float* noise, float guidance_scale,

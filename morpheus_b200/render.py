@@ -233,7 +233,19 @@ class Renderer:
         n1, _ = self.model.normal(surf_pts, t=surf_t)
         w = self.get_ortho_normal_dir(n1, phi)
         n2, _ = self.model.normal(surf_pts + w * tr['smoothness_std'], t=surf_t)
-        return (torch.square(n1 - n2) * keep[:, None]).sum() / (3.0 * keep.sum().clamp(min=1.0))
+        return (torch.square(n1 - n2) * keep[:, None]).sum() / (3.0 * self._gcount(keep.sum()).clamp(min=1.0))
+
+    def _gcount(self, local_count):
+        """data-dependent normaliser under ray sharding: mean over ranks (global_count), so that loss / world_size summed over the
+        ranks is sum / GLOBAL count; the identity on one GPU"""
+        return global_count(local_count, self.world_size) if self.world_size > 1 else local_count
+
+    def _mean_over_samples(self, per_sample_sum, M, fixed):
+        """mean over the packed samples of this shard; with the occupancy sampler M differs per rank, so the divisor is the
+        rank-mean sample count (fixed-S sampling: M is the same on every rank and no collective is needed)"""
+        if self.world_size > 1 and not fixed:
+            return per_sample_sum / self._gcount(torch.tensor(float(M), device=per_sample_sum.device))
+        return per_sample_sum / M
 
     def render_rays(self, rays_o, rays_d, rays_t, rays_id, H=None, W=None, perturb=True, bg_color=None, ambient_ratio=1.0,
                     light_d=None, shading='albedo', real_view=True, cano=False, rays_depth=None, rays_mask=None,
@@ -293,7 +305,9 @@ class Renderer:
             tr = cfg['train']
             if tr['ori_weight'] > 0 and normals is not None and (not real_view):
                 t_dirs = safe_normalize(rays_d[ray_indices])
-                results['loss_orient'] = (weights.detach() * (normals * t_dirs).sum(-1).clamp(min=0) ** 2).sum(-1).mean()
+                # `.sum(-1).mean()` on the [M] tensor (morpheus.py:712) is the SUM over all samples: a shard contributes
+                # world_size x its local sum, so that (loss / world_size) summed over the ranks is the global sum
+                results['loss_orient'] = (weights.detach() * (normals * t_dirs).sum(-1).clamp(min=0) ** 2).sum(-1).mean() * self.world_size
             if tr['normal_smooth_3d'] > 0 and normals is not None:
                 if tr.get('normal_dir', False) or not tr.get('topo_none', True):
                     raise NotImplementedError('normal_dir / topo_none=False branches are disabled in every shipped config')
@@ -301,7 +315,7 @@ class Renderer:
                     perturb_noise = torch.randn_like(xyzs)
                 xyzs_perturb = xyzs + perturb_noise * tr['smoothness_std']
                 normals_perturb, _ = model.normal(xyzs_perturb, topo=None, cano=cano)
-                results['loss_normal_perturb'] = (normals - normals_perturb).abs().mean()
+                results['loss_normal_perturb'] = self._mean_over_samples((normals - normals_perturb).abs().sum(), 3 * xyzs.shape[0], used_uniform)
             if tr['code_reg'] > 0 and not cano:
                 results['loss_code'] = model.code_regulariser(time_step[:1], self.num_frames)      # morpheus.py:762-771, one launch
             if tr.get('normal_smoothness', 0) > 0:

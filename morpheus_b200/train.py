@@ -27,14 +27,18 @@ DEFAULT_TRAIN_CFG = {  # configs/snoopy.yaml:40-94 (only what the step reads)
 FULL_TRAIN_CFG = dict(DEFAULT_TRAIN_CFG, normal_smoothness=0.4, surf_sdf_weight=10.0, surf_color_weight=5.0)   # configs/snoopy.yaml:70-74
 
 
-def surface_point_loss(model, batch, tr):
+def surface_point_loss(model, batch, tr, world_size=1):
     """get_real_view_point_loss, surface terms (morpheus.py:1005-1029): one fused density query (warp + SDF + colour) at the
-    back-projected depth points; SDF^2 averaged over the valid points, colour MSE over all points with invalid ones zeroed."""
+    back-projected depth points; SDF^2 averaged over the valid points, colour MSE over all points with invalid ones zeroed.
+    Under ray sharding the valid-point count is the mean over ranks (render.global_count), so that the summed shard gradients
+    equal the single-GPU gradient."""
+    from .render import global_count
     gt_depth, gt_mask = batch['depth'].reshape(-1), batch['mask'].reshape(-1)
     xyz = batch['rays_o'].reshape(-1, 3) + gt_depth[:, None] * batch['rays_d'].reshape(-1, 3)
     dm = ((gt_depth > 0) & (xyz.norm(dim=-1) <= 1.1) & (gt_mask > 0.5)).float()
     res = model.density(xyz, t=batch['rays_t'].reshape(-1, 1))
-    surf_sdf = tr['surf_sdf_weight'] * (res['sdf'].square() * dm).sum() / dm.sum().clamp(min=1.0)
+    n_valid = global_count(dm.sum(), world_size) if world_size > 1 else dm.sum()
+    surf_sdf = tr['surf_sdf_weight'] * (res['sdf'].square() * dm).sum() / n_valid.clamp(min=1.0)
     surf_col = tr['surf_color_weight'] * F.mse_loss(res['albedo'] * dm[:, None], batch['rgb'] * dm[:, None])
     return surf_sdf + surf_col
 
@@ -63,7 +67,7 @@ class _RayLoss(torch.autograd.Function):
         return (g_i * g, g_o * g, g_d * g) + (None,) * 8
 
 
-def real_view_loss(out, batch, model, tr):
+def real_view_loss(out, batch, model, tr, world_size=1):
     """rgb MSE x5 + mask BCE x.5 + masked depth MSE x.1 (morpheus.py:946-983, one fused launch) + sdf band loss x10 (:991-992)
     + normal_smooth_3d x.1 + code_reg x.5 + beta x.1 (:1116-1142)."""
     pred_rgb = out['image'].reshape(-1, 3)
@@ -81,12 +85,12 @@ def real_view_loss(out, batch, model, tr):
     if 'normal_reg' in out:
         loss = loss + tr['normal_smoothness'] * out['normal_reg']
     if tr.get('surf_sdf_weight', 0) > 0:
-        loss = loss + surface_point_loss(model, batch, tr)
+        loss = loss + surface_point_loss(model, batch, tr, world_size)
     loss = loss + tr['beta_weight'] * torch.mean(model.sdf2density.get_beta())
     return loss
 
 
-def real_view_loss_torch(out, batch, model, tr):
+def real_view_loss_torch(out, batch, model, tr, world_size=1):
     """the same loss as eager torch ops (reference formulation; used by the parity tests)"""
     pred_rgb = out['image'].reshape(-1, 3)
     pred_depth = out['depth'].reshape(-1)
@@ -106,7 +110,7 @@ def real_view_loss_torch(out, batch, model, tr):
     if 'normal_reg' in out:
         loss = loss + tr['normal_smoothness'] * out['normal_reg']
     if tr.get('surf_sdf_weight', 0) > 0:
-        loss = loss + surface_point_loss(model, batch, tr)
+        loss = loss + surface_point_loss(model, batch, tr, world_size)
     loss = loss + tr['beta_weight'] * torch.mean(model.sdf2density.get_beta())
     return loss
 
@@ -160,8 +164,10 @@ class FlatEMA:
     """torch_ema.ExponentialMovingAverage (requirements.txt:24; morpheus.py:160-162, :1299-1301, :1368-1369, :1432-1433) over the
     ONE flat parameter buffer of FlatAdam: update() is a single lerp launch instead of one sub_ per parameter tensor."""
 
-    def __init__(self, flat, decay, use_num_updates=True):
-        self.flat, self.decay = flat, float(decay)
+    def __init__(self, flat, decay, use_num_updates=True, model=None):
+        # `model`: the scene_representation whose parameters are views of `flat`; copy_to / restore / load_state_dict rewrite the
+        # buffer through raw storage (no version-counter bump), so its cached packed arena must be dropped explicitly
+        self.flat, self.decay, self.model = flat, float(decay), model
         self.num_updates = 0 if use_num_updates else None
         self.shadow = flat.detach().clone()
         self.collected = None
@@ -176,12 +182,18 @@ class FlatEMA:
     def store(self):
         self.collected = self.flat.detach().clone()
 
+    def _changed(self):
+        if self.model is not None:
+            self.model.invalidate()
+
     def copy_to(self):
         self.flat.copy_(self.shadow)
+        self._changed()
 
     def restore(self):
         self.flat.copy_(self.collected)
         self.collected = None
+        self._changed()
 
     def state_dict(self):
         return {'decay': self.decay, 'num_updates': self.num_updates, 'shadow': self.shadow, 'collected': self.collected}
@@ -194,8 +206,16 @@ class FlatEMA:
 
 class FlatAdam:
     """All trainable parameters re-homed into ONE flat fp32 buffer (and their .grad into one flat gradient
-    buffer), so a step is: zero one buffer, one all-reduce, one fused Adam launch (csrc/sampler.cu:adam_kernel).
-    Per-group learning rates follow get_params_all() (models/model.py:313-324)."""
+    buffer), so a step is: one all-reduce, one fused Adam launch (csrc/sampler.cu:adam_groups_kernel) that also clears the
+    gradient buffer for the next step.  Per-group learning rates follow get_params_all() (models/model.py:313-324).
+
+    torch.optim.Adam semantics per group (the reference runs torch 2.0: zero_grad() sets .grad to None and Adam SKIPS parameters
+    without a gradient -- no moment decay, no step increment, no move): `set_active()` marks the groups that receive a gradient in
+    the coming step; inactive groups are left untouched and every group carries its own step count for the bias corrections."""
+
+    DEFORM_GROUPS = ('code_deform', 'decoder_deform', 'decoder_topo')
+    # groups that never see a gradient with the shipped flags: bg_net is only reached with cano=True (SURVEY.md 8a-12)
+    NEVER = ('decoder_bg',)
 
     def __init__(self, model, lr, betas=(0.9, 0.99), eps=1e-15):
         groups = model.get_params_all(lr)
@@ -213,24 +233,47 @@ class FlatAdam:
         self.v = torch.zeros(n, device=dev)
         self.group_id = torch.empty(n, dtype=torch.uint8, device=dev)
         off = 0
+        self.group_slices = {}
         for p, gi in zip(plist, gid):
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view(p.shape)
             p.grad = self.grad[off:off + k].view(p.shape)
             self.group_id[off:off + k] = gi
+            a, b = self.group_slices.get(groups[gi]['name'], (off, off))
+            self.group_slices[groups[gi]['name']] = (min(a, off), off + k)
             off += k
         self.group_names = [g['name'] for g in groups]
         self.group_lr = torch.tensor(lrs, device=dev, dtype=torch.float32)
+        self.group_active = torch.ones(len(groups), dtype=torch.uint8, device=dev)
+        self.group_step = torch.zeros(len(groups), dtype=torch.int32, device=dev)     # device-side per-group step counts (graph-replayable)
+        self._active_host = None
         self.betas, self.eps, self.t, self.n = betas, eps, 0, n
-        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # device-side step count (CUDA-graph replayable)
         self.params = plist
         self.model = model
         model.grad_sink = True      # every .grad is a view of self.grad: the kernels accumulate into it directly
         self.current_learning_rate = lr
+        self._clean = True          # the gradient buffer is all zeros (fresh, or cleared by the last fused step)
+        self.set_active(real_view=True)
 
     def set_group_lr(self, name, lr):
         self.group_lr[self.group_names.index(name)] = lr
+
+    def set_active(self, real_view=True, shading='albedo_normal', optimize_pose=None):
+        """Which groups receive a gradient in the coming step (everything else keeps .grad = None in the reference and is skipped by
+        torch.optim.Adam): the pose correction only with optimize_pose (real views, morpheus.py:1418 vs :1399), the colour grid /
+        decoder not under 'textureless' shading (models/model.py:527-529: the albedo does not reach the output), bg_net never."""
+        if optimize_pose is None:
+            optimize_pose = real_view
+        off = set(self.NEVER)
+        if not optimize_pose:
+            off.add('pose')
+        if shading == 'textureless':
+            off.update(('encoder_color', 'decoder_color'))
+        host = tuple(0 if n in off else 1 for n in self.group_names)
+        if host != self._active_host:
+            self.group_active.copy_(torch.tensor(host, dtype=torch.uint8))
+            self._active_host = host
 
     # -- learning-rate schedule of the reference trainer (morpheus.py:471-516), on the device-resident per-group table ------
     def update_learning_rate(self, epoch, tr, scale_factor=1.0):
@@ -239,8 +282,6 @@ class FlatAdam:
         lrs = [self.current_learning_rate * (0.1 if n == 'pose' else 1.0) for n in self.group_names]
         self.group_lr.copy_(torch.tensor(lrs, dtype=torch.float32))
         return self.current_learning_rate
-
-    DEFORM_GROUPS = ('code_deform', 'decoder_deform', 'decoder_topo')
 
     def freeze_lr_deform(self):
         """morpheus.py:504-511 (virtual steps while epoch <= 400 do not move the deformation field)"""
@@ -253,7 +294,10 @@ class FlatAdam:
             self.set_group_lr(n, self.current_learning_rate)
 
     def zero_grad(self):
-        self.grad.zero_()
+        """no launch when the previous fused step already cleared the buffer"""
+        if not self._clean:
+            self.grad.zero_()
+        self._clean = False
 
     def all_reduce(self):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -261,47 +305,60 @@ class FlatAdam:
 
     def step(self):
         self.t += 1
-        self.step_dev += 1
         with _lib.timed('adam'):
-            check(_lib.lib().mb_adam_step_dev(ptr(self.flat), ptr(self.grad), ptr(self.m), ptr(self.v), ptr(self.group_id), ptr(self.group_lr),
-                                              C.c_uint64(self.n), C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
-                                              ptr(self.step_dev), stream()), 'adam_step')
+            check(_lib.lib().mb_adam_step_groups(ptr(self.flat), ptr(self.grad), ptr(self.m), ptr(self.v), ptr(self.group_id), ptr(self.group_lr),
+                                                 ptr(self.group_active), ptr(self.group_step), len(self.group_names), C.c_uint64(self.n),
+                                                 C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps), 1, stream()), 'adam_step_groups')
+        self._clean = True
         self.model.invalidate()    # parameters changed through raw pointers: version counters cannot see it
 
 
-def train_step(renderer, opt, batch, tr, world_size=1, shading='albedo_normal', samples=None):
+def train_step(renderer, opt, batch, tr, world_size=1, shading='albedo_normal', samples=None, **inject):
     """One real-view optimiser step (morpheus.py:1147-1236 + :1415-1424) on this rank's shard of the ray batch.
-    Loss terms are means over the GLOBAL batch: every rank divides by world_size so that the summed
-    all-reduce equals the single-GPU gradient."""
-    model = renderer.model
-    opt.zero_grad()
-    out = renderer.render_rays(batch['rays_o'], batch['rays_d'], batch['rays_t'], batch['rays_id'], bg_color=batch['bg'],
-                               shading=shading, real_view=True, rays_depth=batch['depth'], rays_mask=batch['mask'],
-                               optimize_pose=True, samples=samples)
-    loss = real_view_loss(out, batch, model, tr)
-    (loss / world_size).backward()
+    Loss terms are means over the GLOBAL batch (fixed-size terms divide by world_size, data-dependent counts go through
+    render.global_count) so that the summed all-reduce equals the single-GPU gradient.  `inject`: RNG draws for parity tests
+    (jitter, perturb_noise, light_d)."""
+    loss = train_step_compute(renderer, opt, batch, tr, world_size, shading, samples=samples, **inject)
     opt.all_reduce()
     opt.step()
-    model.invalidate()
-    return loss.detach()
+    return loss
 
 
-def train_step_compute(renderer, opt, batch, tr, world_size=1, shading='albedo_normal'):
-    """zero-grad + render + loss + backward (no collective, no optimiser): the graph-capturable part of a sharded step"""
+def train_step_compute(renderer, opt, batch, tr, world_size=1, shading='albedo_normal', samples=None, **inject):
+    """zero-grad + render + loss + backward (no collective, no optimiser)"""
+    opt.set_active(real_view=True, shading=shading)
     opt.zero_grad()
     out = renderer.render_rays(batch['rays_o'], batch['rays_d'], batch['rays_t'], batch['rays_id'], bg_color=batch['bg'],
-                               shading=shading, real_view=True, rays_depth=batch['depth'], rays_mask=batch['mask'], optimize_pose=True)
-    loss = real_view_loss(out, batch, renderer.model, tr)
+                               shading=shading, real_view=True, rays_depth=batch['depth'], rays_mask=batch['mask'], optimize_pose=True,
+                               samples=samples, **inject)
+    loss = real_view_loss(out, batch, renderer.model, tr, world_size)
     (loss / world_size).backward()
     return loss.detach()
+
+
+def virtual_view_loss_terms(out, model, tr):
+    """get_regularization_loss on a virtual view (morpheus.py:1090-1145 with the shipped weights): orientation
+    x ori_weight (:1119-1120), normal_smooth_3d (:1116-1117), normal_smoothness x normal_reg (:1127-1128 -- NOT gated on real_view),
+    code_reg (:1139-1140), beta (:1124-1125)."""
+    loss = tr['beta_weight'] * torch.mean(model.sdf2density.get_beta())
+    if 'loss_orient' in out:
+        loss = loss + tr['ori_weight'] * out['loss_orient']
+    if 'loss_normal_perturb' in out:
+        loss = loss + tr['normal_smooth_3d'] * out['loss_normal_perturb']
+    if 'normal_reg' in out:
+        loss = loss + tr['normal_smoothness'] * out['normal_reg']
+    if 'loss_code' in out:
+        loss = loss + tr['code_reg'] * out['loss_code']
+    return loss
 
 
 def virtual_view_step(renderer, guidance, opt, view, embeddings, tr, shading='lambertian', ambient_ratio=0.5, bg_color=None,
                       guidance_scale=5.0, grad_weight=0.01, t=None, noise=None, vae_noise=None, light_d=None, world_size=1):
     """One novel-view (SDS) optimiser step: morpheus.py:1147-1236 with real_view=False + get_virtual_view_loss (:1044-1088,
-    single reference view) + the regularisers that are live on virtual views (orientation x ori_weight, normal_smooth_3d,
-    code_reg, beta).  `view` comes from rays.virtual_view_rays."""
+    single reference view) + the regularisers that are live on virtual views (virtual_view_loss_terms).  `view` comes from
+    rays.virtual_view_rays."""
     model = renderer.model
+    opt.set_active(real_view=False, shading=shading)
     opt.zero_grad()
     H, W = view['H'], view['W']
     out = renderer.render_rays(view['rays_o'], view['rays_d'], view['rays_t'], view['rays_id'], H, W, bg_color=bg_color,
@@ -309,52 +366,74 @@ def virtual_view_step(renderer, guidance, opt, view, embeddings, tr, shading='la
     pred_rgb = out['image'].reshape(1, H, W, 3).permute(0, 3, 1, 2).contiguous()
     loss, t, grad_scale, noise = guidance.train_step(embeddings, pred_rgb, view['polar'], view['azimuth'], view['radius'],
                                                      guidance_scale=guidance_scale, grad_scale=grad_weight, t=t, noise=noise, vae_noise=vae_noise)
-    if 'loss_orient' in out:
-        loss = loss + tr['ori_weight'] * out['loss_orient']
-    if 'loss_normal_perturb' in out:
-        loss = loss + tr['normal_smooth_3d'] * out['loss_normal_perturb']
-    if 'loss_code' in out:
-        loss = loss + tr['code_reg'] * out['loss_code']
-    loss = loss + tr['beta_weight'] * torch.mean(model.sdf2density.get_beta())
+    loss = loss + virtual_view_loss_terms(out, model, tr)
     (loss / world_size).backward()
     opt.all_reduce()
     opt.step()
-    model.invalidate()
     return loss.detach(), out
 
 
 class GraphedStep:
-    """The optimiser step captured as CUDA graphs and replayed per iteration: the ~1000 small launches of the host-side
-    glue (parameter packing, indexing, loss heads) cost no CPU time any more.  Inputs live in static device buffers
-    (`self.batch`); shapes are fixed (fixed-S sampler), RNG draws inside the step use torch's graph-safe Philox offsets,
-    the Adam step count is device-resident.  With world_size > 1 the NCCL exchanges stay OUTSIDE the graphs
-    (graph A: zero-grad/render/loss/backward -> eager all-reduce of the flat gradient buffer -> graph B: fused Adam);
-    the global loss normaliser (render.global_count) is reduced eagerly before graph A from the batch itself."""
+    """The real-view optimiser step captured as ONE CUDA graph and replayed per iteration: render + losses + backward, the NCCL
+    all-reduce of the flat gradient buffer (NCCL collectives are stream-ordered and capturable) and the fused Adam (which also
+    clears the gradient buffer for the next replay).  Inputs live in static device buffers (`self.batch`); shapes are fixed
+    (fixed-S sampler), RNG draws inside the step use torch's graph-safe Philox offsets, the Adam step counts are device-resident.
 
-    def __init__(self, renderer, opt, example_batch, tr, world_size=1, warmup=3):
+    Constraint: kernel arguments passed BY VALUE are baked into the graph.  The coarse-to-fine level (`model.max_level` ->
+    n_levels / n_freq, morpheus.py:808-813 rewrites it every step) is such an argument: `step()` compares `model._levels()` with
+    the captured value and RE-CAPTURES when it changed (8 -> 16 grid levels / 3 -> 6 bands: at most 11 re-captures per training).
+    MORPHEUS_B200_GRAPH_NCCL=0 keeps the collective outside (two graphs around an eager all-reduce)."""
+
+    def __init__(self, renderer, opt, example_batch, tr, world_size=1, warmup=3, inject=None):
+        import os
         self.renderer, self.opt, self.tr, self.world = renderer, opt, tr, world_size
         self.batch = {k: v.clone() for k, v in example_batch.items()}
+        # `inject`: static device tensors for the RNG draws of the step (jitter [N], perturb_noise [M,3]; parity tests refill them
+        # in place between replays); None = the step draws them itself (graph-safe Philox offsets)
+        self.inject = inject or {}
         dev = self.batch['rays_o'].device
         if world_size > 1:
             renderer.sdf_count_override = torch.ones((), device=dev)
+        self.nccl_in_graph = world_size > 1 and os.environ.get('MORPHEUS_B200_GRAPH_NCCL', '1') != '0'
+        self.captures = 0
         self._prepare()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                train_step_compute(renderer, opt, self.batch, tr, world_size)
+                train_step_compute(renderer, opt, self.batch, tr, world_size, **self.inject)
                 opt.all_reduce()
                 opt.step()
-                renderer.model.invalidate()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        self._capture()
+
+    def _capture(self):
+        renderer, opt, tr, world = self.renderer, self.opt, self.tr, self.world
+        self.levels = renderer.model._levels()
+        self.graph_b = None
+        if world == 1 or self.nccl_in_graph:
+            try:
+                self.graph_a = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_a):
+                    self.loss = train_step_compute(renderer, opt, self.batch, tr, world, **self.inject)
+                    opt.all_reduce()
+                    opt.step()
+                self.captures += 1
+                return
+            except Exception:
+                if world == 1:
+                    raise
+                self.nccl_in_graph = False       # this NCCL / torch build cannot capture the collective: split the step
+                torch.cuda.synchronize()
+                opt._clean = False
         self.graph_a = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_a):
-            self.loss = train_step_compute(renderer, opt, self.batch, tr, world_size)
+            self.loss = train_step_compute(renderer, opt, self.batch, tr, world, **self.inject)
         self.graph_b = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_b):
             opt.step()
-        renderer.model.invalidate()
+        self.captures += 1
 
     def _prepare(self):
         """global count of samples with a depth observation (utils.py:107 normaliser) for the fixed-S sampler:
@@ -377,8 +456,11 @@ class GraphedStep:
     def step(self, batch=None):
         if batch is not None:
             self.load(batch)
+        if self.renderer.model._levels() != self.levels:
+            self._capture()       # coarse-to-fine level changed: the captured kernels carry the old n_levels / n_freq by value
         self._prepare()
         self.graph_a.replay()
-        self.opt.all_reduce()
-        self.graph_b.replay()
+        if self.graph_b is not None:
+            self.opt.all_reduce()
+            self.graph_b.replay()
         return self.loss

@@ -1,0 +1,299 @@
+"""Whole-step parity (`pytest -m gpu`): the COMPLETE real-view optimiser step the bench times -- pose correction -> fixed-S sampling ->
+fused scene query (albedo_normal) -> compositing -> perturbed-normal regulariser -> loss heads -> backward -> flat gradient -> fused
+Adam (morpheus.py:1147-1236, :1415-1424) -- against `oracle.train_step.step_loss` + torch autograd + torch.optim.Adam with every RNG draw
+injected (stratified jitter, perturbation noise):
+
+  * BASELINE cfg-1 (256 rays x 64 samples) against the CPU oracle;
+  * BASELINE cfg-2 (4096 rays x 128 samples, 13 SDF queries per sample) against the same oracle run in eager torch ON THE GPU with the
+    hash-grid encodes executed by the UNMODIFIED reference CUDA kernel (oracle/_ref, exactly what oracle/ref_gpu_step.py assembles);
+  * eager launches against the CUDA-graph replay (train.GraphedStep), over several steps;
+  * a 2-rank NCCL run whose sharded, all-reduced gradient must equal the single-GPU one (skipped on a 1-GPU box).
+
+Bars: loss rel <= 1e-5, every parameter group's gradient rel-L2 <= 1e-3 (north_star), Adam update equal wherever the gradient is
+not at the noise floor (the first Adam step is lr * sign(g)).
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CONFIG = {'model': {'bg_radius': 1.4, 'activation': 'exp'}, 'render': {'step_size': 0.01}}
+GROUPS = {'encoder_sdf': ['encoder.embeddings'], 'encoder_color': ['encoder_c.embeddings'], 'decoder_sdf': ['sdf_net.'],
+          'decoder_topo': ['topo_net.'], 'decoder_color': ['color_net.'], 'density': ['sdf2density.beta'], 'decoder_deform': ['deform_net.'],
+          'code_deform': ['deform_code.'], 'pose': ['pose_array.data']}
+
+
+def lr_of(name, lr):
+    """initial per-group learning rates of get_params_all (models/model.py:313-324): density lr/2, pose lr/10"""
+    return lr * (0.1 if name == 'pose_array.data' else 0.5 if name == 'sdf2density.beta' else 1.0)
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope='module')
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    return torch.device('cuda:0')
+
+
+def trained_like_state(seed):
+    """sphere-like SDF (rays cross a surface: well-conditioned sigma / weights) whose first SDF layer ALSO reads the hash-grid, frequency
+    and topology features (the pure geometric init zeroes those columns, decoders.py:36-38, and the SDF table would get a zero gradient)"""
+    from oracle.fields import init_reference_like_state
+    sd = init_reference_like_state(200, seed=seed, randomize=True, emb_scale=0.05, sphere=True)
+    g = torch.Generator().manual_seed(seed + 1)
+    w = sd['sdf_net.net.0.weight']
+    w[:, 3:] = w[:, 3:] + 0.05 * torch.randn(w.shape[0], w.shape[1] - 3, generator=g)
+    return sd
+
+
+def build_ours(sd, dev, S, max_level, tr=None):
+    from morpheus_b200 import train as mtrain
+    from morpheus_b200.model import scene_representation
+    from morpheus_b200.nerfacc_compat import OccGridEstimator
+    from morpheus_b200.render import Renderer
+    m = scene_representation(CONFIG, 1.01, num_frames=200, deform_dim=16, use_app=False, use_t=False, amb_dim=2, color_grid=True,
+                             use_joint=True, encode_topo=False)
+    m.load_state_dict(sd, strict=True)
+    m.max_level = max_level
+    m = m.to(dev).train()
+    tr = dict(mtrain.DEFAULT_TRAIN_CFG if tr is None else tr)
+    R = Renderer(m, OccGridEstimator(torch.tensor([-1.01] * 3 + [1.01] * 3), 128).to(dev), dict(CONFIG, train=tr), 200, uniform_samples=S)
+    opt = mtrain.FlatAdam(m, tr['lr'])
+    return m, R, opt, tr
+
+
+def group_grads(named):
+    """{group: flat gradient} from {parameter name: gradient}"""
+    out = {}
+    for gname, prefixes in GROUPS.items():
+        parts = [g.reshape(-1) for n, g in sorted(named.items()) if any(n.startswith(p) for p in prefixes) and g is not None]
+        if parts:
+            out[gname] = torch.cat(parts)
+    return out
+
+
+def compare_step(m, opt, loss, params_o, loss_o, lr, grad_tol=1e-3, min_groups=9):
+    """loss, per-group gradients (opt.grad views) and -- after opt.step() / torch.optim.Adam -- the parameter updates"""
+    assert abs(float(loss) - float(loss_o)) <= 1e-5 * abs(float(loss_o)), (float(loss), float(loss_o))
+    ours = group_grads({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
+    ref = group_grads({n: v.grad for n, v in params_o.items() if v.is_floating_point() and v.grad is not None})
+    errs = {g: rel_l2(ours[g], ref[g]) for g in ref if float(ref[g].abs().max()) > 0}
+    assert len(errs) >= min_groups, errs
+    bad = {g: e for g, e in errs.items() if e > grad_tol}
+    assert not bad, f'gradient rel-L2 above {grad_tol}: {bad}\nall: {errs}'
+    # ---- the optimiser: ours on our gradient, torch.optim.Adam on the oracle's ----
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    opt.step()
+    topt = torch.optim.Adam([{'params': [v], 'lr': lr_of(n, lr)} for n, v in params_o.items()
+                             if v.is_floating_point() and v.requires_grad], lr=lr, betas=(0.9, 0.99), eps=1e-15)
+    before_o = {n: v.detach().clone() for n, v in params_o.items() if v.is_floating_point()}
+    topt.step()
+    for n, p in m.named_parameters():
+        g_o = params_o[n].grad
+        d_ours = (p.detach() - before[n]).cpu()
+        if g_o is None:            # torch skips parameters without a gradient (bg_net): ours must not move them either
+            assert float(d_ours.abs().max()) == 0.0, n
+            continue
+        d_ref = (params_o[n].detach() - before_o[n]).cpu()
+        g_o = g_o.cpu()
+        live = g_o.abs() > 1e-2 * g_o.abs().max()         # first Adam step = lr * sign(g): compare away from the sign-flip noise floor
+        if live.any():
+            step = lr_of(n, lr)
+            assert float((d_ours - d_ref)[live].abs().max()) <= 1e-3 * step, (n, float((d_ours - d_ref)[live].abs().max()))
+    assert float(opt.grad.abs().max()) == 0.0          # the fused step cleared the gradient buffer for the next iteration
+    return errs
+
+
+def test_whole_step_cfg1_vs_cpu_oracle(dev):
+    """BASELINE configs[0]: 256 rays x 64 samples, full 13-query real-view step, CPU oracle autograd as the checker."""
+    from morpheus_b200 import train as mtrain
+    from morpheus_b200.rays import synthetic_real_view_batch
+    from oracle import train_step as ots
+    N, S, ML = 256, 64, 0.8
+    sd = trained_like_state(21)
+    batch = synthetic_real_view_batch(N, seed=5, frame=63)
+    g = torch.Generator().manual_seed(9)
+    jitter = torch.rand(N, generator=g)
+    noise = torch.randn(N * S, 3, generator=g)
+    params_o = ots.make_params(sd)
+    loss_o, _ = ots.step_loss(params_o, batch, S, ML, jitter=jitter, perturb_noise=noise)
+    loss_o.backward()
+    m, R, opt, tr = build_ours(sd, dev, S, ML)
+    b = {k: v.to(dev) for k, v in batch.items()}
+    loss = mtrain.train_step_compute(R, opt, b, tr, jitter=jitter.to(dev), perturb_noise=noise.to(dev))
+    errs = compare_step(m, opt, loss, params_o, loss_o, tr['lr'])
+    print('cfg-1 gradient rel-L2 per group:', {k: f'{v:.1e}' for k, v in errs.items()})
+
+
+def _gpu_oracle(dev):
+    """oracle.train_step on the GPU with the reference CUDA kernel for the hash-grid encodes (oracle/ref_gpu_step.py)"""
+    from oracle import fields as of
+    from oracle import ref_gpu_step as rgs
+    backend = rgs.load_ref_backend()
+    if backend is None:
+        pytest.skip('oracle/_ref not built (needs /root/reference at build time)')
+    grid_fn = rgs.make_grid_fn(backend)
+    orig = of.SceneOracle.grid
+
+    def grid(self, which, x):
+        u = (x + self.bound) / (2 * self.bound)
+        return grid_fn.apply(u, self.sd[which + '.embeddings'], self.sd[which + '.offsets'], self.S, self.H, u.requires_grad, self.max_level)
+    return grid, orig
+
+
+def test_whole_step_cfg2_vs_reference_kernel_oracle(dev):
+    """BASELINE configs[1]: 4096 rays x 128 samples (M = 524 288: 4096 tiles, every persistent CTA loops over many tiles), against the
+    eager-torch oracle on the GPU + the reference grid kernel.  Three consecutive steps: eager launches and the CUDA-graph replay must
+    both follow the oracle's loss trajectory (each loss depends on the previous steps' updates)."""
+    from morpheus_b200 import train as mtrain
+    from morpheus_b200.rays import synthetic_real_view_batch
+    from oracle import fields as of
+    from oracle import train_step as ots
+    N, S, ML = 4096, 128, 1.0
+    sd = trained_like_state(22)
+    batches = [synthetic_real_view_batch(N, seed=40 + i, frame=(17 * i + 3) % 200) for i in range(3)]
+    g = torch.Generator().manual_seed(10)
+    jit = [torch.rand(N, generator=g) for _ in range(3)]
+    noi = [torch.randn(N * S, 3, generator=g) for _ in range(3)]
+    grid, orig = _gpu_oracle(dev)
+    of.SceneOracle.grid = grid
+    try:
+        with torch.device(dev):
+            params_o = ots.make_params({k: v.to(dev) for k, v in sd.items()})
+            lr = mtrain.DEFAULT_TRAIN_CFG['lr']
+            topt = torch.optim.Adam([{'params': [v], 'lr': lr_of(n, lr)} for n, v in params_o.items()
+                                     if v.is_floating_point() and v.requires_grad], lr=lr, betas=(0.9, 0.99), eps=1e-15)
+            losses_o, grads_o = [], None
+            for i in range(3):
+                topt.zero_grad()
+                loss_o, _ = ots.step_loss(params_o, {k: v.to(dev) for k, v in batches[i].items()}, S, ML, jitter=jit[i].to(dev), perturb_noise=noi[i].to(dev))
+                loss_o.backward()
+                if i == 0:
+                    grads_o = {n: (v.grad.clone() if v.is_floating_point() and v.grad is not None else None) for n, v in params_o.items()}
+                    loss0_o = loss_o.detach().clone()
+                topt.step()
+                losses_o.append(float(loss_o))
+    finally:
+        of.SceneOracle.grid = orig
+    del params_o, topt
+    torch.cuda.empty_cache()
+
+    # ---- ours, eager: step-0 loss + gradients + Adam update, then the trajectory ----
+    m, R, opt, tr = build_ours(sd, dev, S, ML)
+    dbatches = [{k: v.to(dev) for k, v in b.items()} for b in batches]
+    loss = mtrain.train_step_compute(R, opt, dbatches[0], tr, jitter=jit[0].to(dev), perturb_noise=noi[0].to(dev))
+    assert abs(float(loss) - losses_o[0]) <= 1e-5 * abs(losses_o[0]), (float(loss), losses_o[0])
+    ours = group_grads({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
+    ref = group_grads({n: v for n, v in grads_o.items() if v is not None})
+    errs = {k: rel_l2(ours[k], ref[k]) for k in ref if float(ref[k].abs().max()) > 0}
+    print('cfg-2 gradient rel-L2 per group:', {k: f'{v:.1e}' for k, v in errs.items()})
+    assert len(errs) >= 9, errs
+    bad = {k: e for k, e in errs.items() if e > 1e-3}
+    assert not bad, f'{bad}\nall: {errs}'
+    opt.step()
+    losses = [float(loss)]
+    for i in (1, 2):
+        losses.append(float(mtrain.train_step(R, opt, dbatches[i], tr, jitter=jit[i].to(dev), perturb_noise=noi[i].to(dev))))
+    # losses 1, 2 depend on the Adam updates (lr * sign(g) on the first step: a few noise-floor elements may differ) -> 1e-4
+    for a, b in zip(losses, losses_o):
+        assert abs(a - b) <= 1e-4 * abs(b), (losses, losses_o)
+
+    # ---- ours, CUDA graph: same three steps through GraphedStep with the draws in static buffers ----
+    m2, R2, opt2, tr2 = build_ours(sd, dev, S, ML)
+    inject = {'jitter': jit[0].to(dev).clone(), 'perturb_noise': noi[0].to(dev).clone()}
+    state0 = opt2.flat.clone()
+    gs = mtrain.GraphedStep(R2, opt2, dbatches[0], tr2, 1, inject=inject)
+    # the warm-up steps of the capture moved the parameters: rewind parameters and optimiser state
+    opt2.flat.copy_(state0); opt2.m.zero_(); opt2.v.zero_(); opt2.grad.zero_(); opt2.group_step.zero_()
+    m2.invalidate()
+    losses_g = []
+    for i in range(3):
+        inject['jitter'].copy_(jit[i].to(dev)); inject['perturb_noise'].copy_(noi[i].to(dev))
+        losses_g.append(float(gs.step(dbatches[i])))
+    for a, b in zip(losses_g, losses_o):
+        assert abs(a - b) <= 1e-4 * abs(b), (losses_g, losses_o)
+    assert rel_l2(opt2.flat, opt.flat) < 1e-4          # same parameters after three steps, eager vs replay
+    print('losses oracle / eager / graph:', losses_o, losses, losses_g)
+
+
+def test_graphed_step_recaptures_on_level_change(dev):
+    """coarse-to-fine: model.max_level changes between steps (morpheus.py:808-813); the graph carries n_levels / n_freq by value and
+    must be re-captured, otherwise training silently stays at the capture-time level."""
+    from morpheus_b200 import train as mtrain
+    from morpheus_b200.rays import synthetic_real_view_batch
+    N, S = 256, 32
+    sd = trained_like_state(23)
+    m, R, opt, tr = build_ours(sd, dev, S, 0.5)
+    b = {k: v.to(dev) for k, v in synthetic_real_view_batch(N, seed=3).items()}
+    g = torch.Generator().manual_seed(1)
+    inject = {'jitter': torch.rand(N, generator=g).to(dev), 'perturb_noise': torch.randn(N * S, 3, generator=g).to(dev)}
+    gs = mtrain.GraphedStep(R, opt, b, tr, 1, inject=inject)
+    assert gs.captures == 1
+    m.max_level = 0.51           # same level count: no re-capture
+    gs.step(b)
+    assert gs.captures == 1
+    m.max_level = 0.9            # ceil(0.9 * 16) = 15 levels, 5 bands
+    state = opt.flat.clone()
+    mstate, vstate, sstate = opt.m.clone(), opt.v.clone(), opt.group_step.clone()
+    l_graph = float(gs.step(b))
+    assert gs.captures == 2 and gs.levels == (15, 5)
+    # the same step eagerly from the same state
+    opt.flat.copy_(state); opt.m.copy_(mstate); opt.v.copy_(vstate); opt.group_step.copy_(sstate); opt.grad.zero_()
+    m.invalidate()
+    l_eager = float(mtrain.train_step(R, opt, b, tr, **inject))
+    assert abs(l_graph - l_eager) <= 1e-5 * abs(l_eager), (l_graph, l_eager)
+
+
+def test_adam_skips_groups_without_gradient(dev):
+    """torch.optim.Adam skips parameters whose .grad is None (torch >= 2.0 zero_grad): virtual-view steps must not move the pose
+    correction with stale momentum, 'textureless' steps must not move the colour grid / decoder, bg_net never moves."""
+    from morpheus_b200 import train as mtrain
+    sd = trained_like_state(24)
+    m, R, opt, tr = build_ours(sd, dev, 32, 1.0)
+    g = torch.Generator().manual_seed(2)
+    # reference: torch Adam over the same flat tensors, with the same "gradient present" pattern
+    ref_p = {n: p.detach().clone().requires_grad_(True) for n, p in m.named_parameters()}
+    topt = torch.optim.Adam([{'params': [v], 'lr': lr_of(n, tr['lr'])} for n, v in ref_p.items()], lr=tr['lr'],
+                            betas=(0.9, 0.99), eps=1e-15)
+    steps = [dict(real_view=True, shading='albedo_normal'), dict(real_view=False, shading='lambertian'), dict(real_view=False, shading='textureless'),
+             dict(real_view=True, shading='albedo_normal')]
+    for st in steps:
+        opt.set_active(**st)
+        skip = ['bg_net.']
+        if not st['real_view']:
+            skip.append('pose_array.')
+        if st['shading'] == 'textureless':
+            skip += ['encoder_c.', 'color_net.']
+        for n, p in m.named_parameters():
+            gr = torch.randn(p.shape, generator=g).to(dev) * 1e-3
+            if any(n.startswith(s) for s in skip):
+                ref_p[n].grad = None
+            else:
+                p.grad.copy_(gr)          # .grad is a view of the flat gradient buffer
+                ref_p[n].grad = gr.clone()
+        opt._clean = False
+        opt.step()
+        topt.step()
+        for n, p in m.named_parameters():
+            assert torch.allclose(p.detach(), ref_p[n].detach(), rtol=0, atol=2e-7), (st, n, float((p.detach() - ref_p[n].detach()).abs().max()))
+
+
+def test_two_rank_sharded_gradient_equals_single_gpu(dev):
+    """ray-sharded step on 2 GPUs (NCCL): the all-reduced flat gradient equals the single-GPU gradient."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (gpurun --gpus 2)')
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+                          '--master-port', '29631', os.path.join(ROOT, 'tests', 'dist_step_worker.py')], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert 'SHARDED_OK' in out.stdout, out.stdout[-3000:]
