@@ -109,5 +109,9 @@ def test_virtual_view_step_end_to_end():
                                          bg_color=torch.rand(3, device=dev))
     torch.cuda.synchronize()
     assert out['image'].shape == (1, 72 * 72, 3) and torch.isfinite(loss)
-    assert torch.isfinite(opt.grad).all() and float(opt.grad.abs().max()) > 0
-    assert float((opt.flat - before).abs().max()) > 0
+    # (the fused Adam launch clears the gradient buffer: the SDS gradient is observed through the parameter updates)
+    assert torch.isfinite(opt.flat).all() and float(opt.grad.abs().max()) == 0
+    moved = {n: float((opt.flat[a:b] - before[a:b]).abs().max()) for n, (a, b) in opt.group_slices.items()}
+    for n in ('encoder_sdf', 'encoder_color', 'decoder_sdf', 'decoder_color', 'decoder_deform', 'decoder_topo', 'density'):
+        assert moved[n] > 0, moved
+    assert moved['pose'] == 0 and moved['decoder_bg'] == 0, moved      # no gradient on a virtual view: torch.optim.Adam skips them

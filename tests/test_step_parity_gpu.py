@@ -54,6 +54,11 @@ def trained_like_state(seed):
     g = torch.Generator().manual_seed(seed + 1)
     w = sd['sdf_net.net.0.weight']
     w[:, 3:] = w[:, 3:] + 0.05 * torch.randn(w.shape[0], w.shape[1] - 3, generator=g)
+    # Laplace density conditioning: d(ln sigma) = (|s| / beta) d(ln s).  With the init helper's beta = 0.05 the oracle's own fp32
+    # rounding of the SDF (~1e-6) is amplified to 5e-5 on opacity / depth / mask loss (measured: sdf rel 1.5e-6 -> weights_sum 5.5e-5,
+    # loss 2.9e-5: tools/debug_step.py), i.e. the comparison would measure the scene's conditioning, not the kernels.  beta = 0.3
+    # (|s| <~ 5 beta along the AABB chord) keeps the strict 1e-5 loss bar meaningful.
+    sd['sdf2density.beta'] = torch.tensor(0.3)
     return sd
 
 
