@@ -39,7 +39,7 @@ def step_loss(params, batch, n_samples, max_level, tr=TRAIN_CFG, num_frames=200,
                           perturb_noise=perturb_noise, trunc=tr['trunc'], smoothness_std=tr['smoothness_std'], training=True, real_view=True)
     gt_depth, gt_mask = batch['depth'].reshape(-1), batch['mask'].reshape(-1)
     loss = tr['rgb_weight'] * F.mse_loss(out['image'], batch['rgb'])
-    loss = loss + tr['mask_weight'] * F.binary_cross_entropy(out['weights_sum'].reshape(-1).clip(1e-5, 1 - 1e-5), gt_mask.float())
+    loss = loss + tr['mask_weight'] * F.binary_cross_entropy(out['weights_sum'].reshape(-1).clip(1e-5, 1 - 1e-5), gt_mask.to(out['weights_sum'].dtype))
     xyz = batch['rays_o'] + gt_depth[:, None] * batch['rays_d']
     dm = ((gt_depth > 0) & (xyz.norm(dim=-1) <= 1.1) & (gt_mask > 0.5)).float()
     loss = loss + tr['depth_weight'] * F.mse_loss(out['depth'] * dm, gt_depth * dm)

@@ -120,25 +120,52 @@ def compare_step(m, opt, loss, params_o, loss_o, lr, grad_tol=1e-3, min_groups=9
     return errs
 
 
+def cpu_oracle_step(sd, batch, S, ML, jitter, noise, dtype):
+    """oracle.train_step on the CPU in `dtype` (autograd gradients populated) -> (params, loss)"""
+    from oracle import train_step as ots
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        params = ots.make_params({k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()})
+        b = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in batch.items()}
+        loss, _ = ots.step_loss(params, b, S, ML, jitter=jitter.to(dtype), perturb_noise=noise.to(dtype))
+        loss.backward()
+    finally:
+        torch.set_default_dtype(prev)
+    return params, loss.detach()
+
+
 def test_whole_step_cfg1_vs_cpu_oracle(dev):
-    """BASELINE configs[0]: 256 rays x 64 samples, full 13-query real-view step, CPU oracle autograd as the checker."""
+    """BASELINE configs[0]: 256 rays x 64 samples, full 13-query real-view step, coarse-to-fine level 0.8 (13 grid levels, 4 bands).
+    The checker is the CPU oracle evaluated in FLOAT64: at this size the fp32 oracle itself is 6e-3 / 9e-4 / 1.4e-3 away from its
+    fp64 value on the SDF-table / SDF-decoder / pose gradients (the +-eps finite-difference rows scatter nearly cancelling
+    contributions), so an fp32-vs-fp32 comparison would measure the checker's rounding, not the kernels.  The fp32 oracle's own
+    deviation is printed next to ours."""
     from morpheus_b200 import train as mtrain
     from morpheus_b200.rays import synthetic_real_view_batch
-    from oracle import train_step as ots
     N, S, ML = 256, 64, 0.8
     sd = trained_like_state(21)
     batch = synthetic_real_view_batch(N, seed=5, frame=63)
     g = torch.Generator().manual_seed(9)
     jitter = torch.rand(N, generator=g)
     noise = torch.randn(N * S, 3, generator=g)
-    params_o = ots.make_params(sd)
-    loss_o, _ = ots.step_loss(params_o, batch, S, ML, jitter=jitter, perturb_noise=noise)
-    loss_o.backward()
+    params_o, loss_o = cpu_oracle_step(sd, batch, S, ML, jitter, noise, torch.float64)
+    params_32, loss_32 = cpu_oracle_step(sd, batch, S, ML, jitter, noise, torch.float32)
+    g64 = group_grads({n: v.grad for n, v in params_o.items() if v.is_floating_point() and v.grad is not None})
+    g32 = group_grads({n: v.grad for n, v in params_32.items() if v.is_floating_point() and v.grad is not None})
+    floor = {k: rel_l2(g32[k], g64[k]) for k in g64}
     m, R, opt, tr = build_ours(sd, dev, S, ML)
     b = {k: v.to(dev) for k, v in batch.items()}
     loss = mtrain.train_step_compute(R, opt, b, tr, jitter=jitter.to(dev), perturb_noise=noise.to(dev))
+    for v in params_o.values():       # the Adam comparison runs in fp32 on the fp64 gradients
+        if v.is_floating_point():
+            v.data = v.data.float()
+            if v.grad is not None:
+                v.grad = v.grad.float()
     errs = compare_step(m, opt, loss, params_o, loss_o, tr['lr'])
-    print('cfg-1 gradient rel-L2 per group:', {k: f'{v:.1e}' for k, v in errs.items()})
+    print('cfg-1 gradient rel-L2 vs fp64 oracle, ours:', {k: f'{v:.1e}' for k, v in errs.items()})
+    print('cfg-1 gradient rel-L2 vs fp64 oracle, fp32 oracle:', {k: f'{v:.1e}' for k, v in floor.items()},
+          'loss', abs(float(loss_32) - float(loss_o)) / abs(float(loss_o)))
 
 
 def _gpu_oracle(dev):
@@ -239,13 +266,13 @@ def test_graphed_step_recaptures_on_level_change(dev):
     from morpheus_b200.rays import synthetic_real_view_batch
     N, S = 256, 32
     sd = trained_like_state(23)
-    m, R, opt, tr = build_ours(sd, dev, S, 0.5)
+    m, R, opt, tr = build_ours(sd, dev, S, 0.55)
     b = {k: v.to(dev) for k, v in synthetic_real_view_batch(N, seed=3).items()}
     g = torch.Generator().manual_seed(1)
     inject = {'jitter': torch.rand(N, generator=g).to(dev), 'perturb_noise': torch.randn(N * S, 3, generator=g).to(dev)}
     gs = mtrain.GraphedStep(R, opt, b, tr, 1, inject=inject)
     assert gs.captures == 1
-    m.max_level = 0.51           # same level count: no re-capture
+    m.max_level = 0.56           # same level count (9 levels, 3 bands): no re-capture
     gs.step(b)
     assert gs.captures == 1
     m.max_level = 0.9            # ceil(0.9 * 16) = 15 levels, 5 bands
