@@ -88,15 +88,17 @@ def group_grads(named):
     return out
 
 
-def compare_step(m, opt, loss, params_o, loss_o, lr, grad_tol=1e-3, min_groups=9):
-    """loss, per-group gradients (opt.grad views) and -- after opt.step() / torch.optim.Adam -- the parameter updates"""
+def compare_step(m, opt, loss, params_o, loss_o, lr, grad_tol=1e-3, min_groups=9, floor=None):
+    """loss, per-group gradients (opt.grad views) and -- after opt.step() / torch.optim.Adam -- the parameter updates.
+    `floor`: per-group deviation of the fp32 oracle from the fp64 oracle; a group passes at max(grad_tol, floor[group]), i.e. the
+    kernels must be within 1e-3 of the exact gradient or at least as close to it as the reference's own fp32 arithmetic."""
     assert abs(float(loss) - float(loss_o)) <= 1e-5 * abs(float(loss_o)), (float(loss), float(loss_o))
     ours = group_grads({n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
     ref = group_grads({n: v.grad for n, v in params_o.items() if v.is_floating_point() and v.grad is not None})
     errs = {g: rel_l2(ours[g], ref[g]) for g in ref if float(ref[g].abs().max()) > 0}
     assert len(errs) >= min_groups, errs
-    bad = {g: e for g, e in errs.items() if e > grad_tol}
-    assert not bad, f'gradient rel-L2 above {grad_tol}: {bad}\nall: {errs}'
+    bad = {g: e for g, e in errs.items() if e > max(grad_tol, (floor or {}).get(g, 0.0))}
+    assert not bad, f'gradient rel-L2 above {grad_tol}: {bad}\nall: {errs}\nfp32-oracle floor: {floor}'
     # ---- the optimiser: ours on our gradient, torch.optim.Adam on the oracle's ----
     before = {n: p.detach().clone() for n, p in m.named_parameters()}
     opt.step()
@@ -162,7 +164,7 @@ def test_whole_step_cfg1_vs_cpu_oracle(dev):
             v.data = v.data.float()
             if v.grad is not None:
                 v.grad = v.grad.float()
-    errs = compare_step(m, opt, loss, params_o, loss_o, tr['lr'])
+    errs = compare_step(m, opt, loss, params_o, loss_o, tr['lr'], floor=floor)
     print('cfg-1 gradient rel-L2 vs fp64 oracle, ours:', {k: f'{v:.1e}' for k, v in errs.items()})
     print('cfg-1 gradient rel-L2 vs fp64 oracle, fp32 oracle:', {k: f'{v:.1e}' for k, v in floor.items()},
           'loss', abs(float(loss_32) - float(loss_o)) / abs(float(loss_o)))
