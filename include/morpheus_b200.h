@@ -193,6 +193,19 @@ int mb_field_backward_fd_tc(const mb_field_params* p, const mb_field_io* io, con
                             const uint32_t* tc_off, const void* tc_weights_t, const uint32_t* tc_off_t, int accumulate, mb_stream_t stream);
 /* debug: cumulative clock64 cycles per phase of mb_field_backward_fd_tc, summed over CTAs (16 host words); reset != 0 clears */
 int mb_debug_fd_phases(unsigned long long* host_out16, int reset);
+/* Fused finite-difference normal regulariser of a real-view step: loss_normal_perturb of MorpheuS.render_rays (morpheus.py:714-741) =
+ * mean |n(x, topo) - n(x + noise * noise_std, topo = 0)| with n = safe_normalize(6-point FD of the SDF, models/model.py:367-398), forward
+ * AND backward in one launch (csrc/field_fd_reg_tc.cu).  Valid when the colour does not depend on the normal ('albedo_normal', ratio 1).
+ *   loss[0]   += gmul * sum_{samples, axes} |n - n_p|                    (caller zero-fills; gmul = 1 / (3 M) gives the mean)
+ *   normal / normal_raw [M,3]  the unperturbed set's normals (nullable)
+ *   g_x [M,3], g_topo [M,2]    d loss / d x, d loss / d topo (written; g_topo required iff topo != NULL)
+ *   g_emb_sdf, g_arena         d loss / d (SDF hash table), d loss / d (packed arena: sdf layers) ACCUMULATED (red.global.add)
+ * noise may be NULL (zeros).  tc_* as for mb_field_backward_fd_tc. */
+int mb_fd_regulariser_tc(const mb_field_params* p, const float* x, const float* topo, const float* noise, float noise_std, uint32_t M,
+                         float gmul, float* normal, float* normal_raw, float* loss, float* g_x, float* g_topo, float* g_emb_sdf,
+                         float* g_arena, const void* tc_weights, const uint32_t* tc_off, const void* tc_weights_t, const uint32_t* tc_off_t,
+                         mb_stream_t stream);
+
 int mb_field_backward_warp_tc(const mb_field_params* p, const float* x, const float* t, uint32_t M, const float* g_def,
                               const float* g_topo, const void* stash, const void* tc_weights_t, const uint32_t* tc_off_t,
                               float* g_arena, float* const g_code[3], float* g_x, mb_stream_t stream);

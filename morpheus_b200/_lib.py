@@ -22,6 +22,8 @@ USE_TC_BWD = os.environ.get('MORPHEUS_B200_TC_BWD', '1') != '0'
 USE_TC_BWD_SDF = os.environ.get('MORPHEUS_B200_TC_BWD_SDF', '1') != '0'
 # FD-normal queries of the backward in the specialised two-CTAs-per-SM kernel (csrc/field_bwd_fd_tc.cu)
 USE_TC_BWD_FD = os.environ.get('MORPHEUS_B200_TC_BWD_FD', '1') != '0'
+# real-view FD-normal regulariser (both FD sets of a sample, forward + backward) in ONE launch (csrc/field_fd_reg_tc.cu)
+USE_FD_REG = os.environ.get('MORPHEUS_B200_FD_REG', '1') != '0'
 
 
 class LayerDesc(C.Structure):
@@ -63,7 +65,7 @@ SYMBOLS = ['mb_version', 'mb_last_error', 'mb_sm_count', 'mb_grid_encode_forward
            'mb_composite_backward', 'mb_field_forward', 'mb_field_backward', 'mb_occ_update', 'mb_occ_binarize',
            'mb_adam_step', 'mb_sds_grad', 'mb_add_noise', 'mb_pack_tc', 'mb_field_forward_tc', 'mb_adam_step_dev', 'mb_adam_step_groups', 'mb_field_backward_warp_tc', 'mb_field_backward_sdf_tc',
            'mb_ray_points_forward', 'mb_ray_points_backward', 'mb_pack_arena_forward', 'mb_pack_arena_backward', 'mb_sdf_loss_forward',
-           'mb_sdf_loss_backward', 'mb_pose_rays_forward', 'mb_pose_rays_backward', 'mb_ray_loss', 'mb_field_backward_fd_tc', 'mb_debug_fd_phases', 'mb_code_reg']
+           'mb_sdf_loss_backward', 'mb_pose_rays_forward', 'mb_pose_rays_backward', 'mb_ray_loss', 'mb_field_backward_fd_tc', 'mb_fd_regulariser_tc', 'mb_debug_fd_phases', 'mb_code_reg']
 
 
 def lib():

@@ -467,6 +467,55 @@ class _FieldQuery(torch.autograd.Function):
         return (None, g_x, None, None, g_topo_in, g_arena, g_es, g_ec, gc[0], gc[1], gc[2], g_beta.reshape(()))
 
 
+class _FDRegulariser(torch.autograd.Function):
+    """loss_normal_perturb of MorpheuS.render_rays (morpheus.py:714-741) on a real view, forward AND backward in ONE launch
+    (mb_fd_regulariser_tc, csrc/field_fd_reg_tc.cu): both 6-point FD normals of every sample (at x with the sample's topo, at
+    x + noise * std with topo = 0), the L1 difference, and its gradients w.r.t. the SDF hash table, the SDF decoder, x and topo.
+    The launch computes the gradients of the returned scalar; backward() only scales them by the upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, cfg, x, topo, noise, arena, emb_sdf):
+        n_levels, n_freq, offsets, bound, S, H, tcws, sink_emb, noise_std, gmul = cfg
+        M = x.shape[0]
+        dev = x.device
+        x = x.contiguous().float()
+        topo_c = topo.contiguous().float() if topo is not None else None
+        noise_c = noise.contiguous().float() if noise is not None else None
+        P = packing.fill_descs(_lib.FieldParams())
+        P.arena = ptr(arena.detach())
+        P.emb_sdf, P.offsets = ptr(emb_sdf.detach()), ptr(offsets)
+        P.bound, P.two_bound, P.S, P.H = bound, float(2 * bound), S, H
+        P.n_levels, P.n_freq = n_levels, n_freq
+        normal = torch.empty(M, 3, device=dev, dtype=torch.float32)
+        normal_raw = torch.empty(M, 3, device=dev, dtype=torch.float32)
+        loss = torch.zeros(1, device=dev, dtype=torch.float32)
+        g_x = torch.empty(M, 3, device=dev, dtype=torch.float32)
+        g_topo = torch.empty(M, 2, device=dev, dtype=torch.float32) if topo is not None else None
+        g_emb = torch.zeros_like(emb_sdf)
+        g_arena = torch.zeros_like(arena)
+        tabs_f, tabs_s = _tc_tables(dev), _tc_tables_small(dev)
+        with _lib.timed('fd_regulariser'):
+            check(_lib.lib().mb_fd_regulariser_tc(_lib.C.byref(P), ptr(x), ptr(topo_c), ptr(noise_c), _lib.C.c_float(noise_std), M, _lib.C.c_float(gmul),
+                                                  ptr(normal), ptr(normal_raw), ptr(loss), ptr(g_x), ptr(g_topo), ptr(g_emb), ptr(g_arena),
+                                                  ptr(tcws['f']), ptr(tabs_f[1]), ptr(tcws['s']), ptr(tabs_s[1]), stream()), 'fd_regulariser_tc')
+        ctx.sink_emb = sink_emb
+        ctx.has_topo = topo is not None
+        ctx.save_for_backward(g_x, g_topo, g_emb, g_arena)
+        ctx.mark_non_differentiable(normal, normal_raw)
+        return loss[0], normal, normal_raw
+
+    @staticmethod
+    def backward(ctx, g_loss, _gn, _gr):
+        g_x, g_topo, g_emb, g_arena = ctx.saved_tensors
+        g = g_loss.reshape(())
+        if ctx.sink_emb is not None:       # train.FlatAdam: straight into the table's .grad view of the flat gradient buffer
+            ctx.sink_emb.addcmul_(g_emb, g)
+            g_emb_out = None
+        else:
+            g_emb_out = g_emb * g
+        return None, g_x * g, (g_topo * g if ctx.has_topo else None), None, g_arena * g, g_emb_out
+
+
 # ------------------------------------------------------------------------------------------------
 class scene_representation(nn.Module):
     def __init__(self, config, bound, max_level=None, num_layers=3, num_layers_t=6, hidden_dim=64, hidden_dim_t=128,
@@ -690,6 +739,28 @@ class scene_representation(nn.Module):
         R = self.pose_array.get_rotation_matrices(frame_ids)
         tr = self.pose_array.get_translations(frame_ids)
         return rays_o + tr, torch.sum(rays_d[..., None, :] * R, -1)
+
+    def fd_regulariser(self, x, topo, noise, noise_std, gmul):
+        """Real-view normal regulariser in one fused launch: -> (gmul * sum |n(x, topo) - n(x + noise * std, 0)|, n, n_raw) with
+        n = normal(x, topo) of models/model.py:387-398 and the perturbed query of morpheus.py:724-736 (topo_none).  Tensor-core engine only."""
+        if not _lib.USE_TC:
+            raise RuntimeError('morpheus_b200: fd_regulariser needs the tensor-core engine (MORPHEUS_B200_TC=1)')
+        if x.shape[0] == 0:
+            raise RuntimeError('morpheus_b200: empty query')
+        n_levels, n_freq = self._levels()
+        enc = self.encoder
+        arena, tcw = self.packed_arena()
+        if tcw is None:
+            tcw = self._pack_tc(arena.detach())
+        sinks = self._sinks()
+        cfg = (n_levels, n_freq, enc.offsets, float(self.bound), float(np.log2(enc.per_level_scale)), int(enc.base_resolution), tcw,
+               sinks[0] if sinks is not None else None, float(noise_std), float(gmul))
+        return _FDRegulariser.apply(cfg, x, topo, noise, arena, enc.embeddings)
+
+    def forward_with_topo(self, x, t):
+        """forward(x, t, shading='albedo') plus the topology coordinates of the warp (differentiable): -> (sdf, sigma, albedo, deform, topo)"""
+        out = self._query(x, t, F_MAIN | F_COLOR | F_WARP)
+        return out[0], out[1], out[2], out[5], out[6]
 
     def density(self, x, t=None, cano=False, allow_shape=False, return_color=True):
         """model.py:439-481"""

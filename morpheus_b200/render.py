@@ -289,7 +289,23 @@ class Renderer:
             weights = opacity = normals = deform = normal_raw = None
         else:
             light = light_d[ray_indices] if shading != 'albedo' else None
-            sdf, sigmas, rgbs, normals, deform, normal_raw = model(xyzs, time_step, light, ratio=ambient_ratio, shading=shading, cano=cano)
+            tr_ = cfg.get('train', {}) if model.training else {}
+            # real-view training step: with 'albedo_normal' (ratio 1) the colour does not depend on the normal, so the two FD-normal
+            # sets of a sample (at x, and at the perturbed point) only feed loss_normal_perturb: ONE fused forward+backward launch
+            fused_fd = (_lib.USE_TC and _lib.USE_FD_REG and model.training and torch.is_grad_enabled() and real_view and not cano
+                        and shading == 'albedo_normal' and float(ambient_ratio) == 1.0 and tr_.get('normal_smooth_3d', 0) > 0
+                        and not tr_.get('normal_dir', False) and tr_.get('topo_none', True))
+            if fused_fd:
+                sdf, sigmas, rgbs, deform, topo_w = model.forward_with_topo(xyzs, time_step)
+                if perturb_noise is None:
+                    perturb_noise = torch.randn_like(xyzs)
+                M_ = xyzs.shape[0]
+                l_np, normals, normal_raw = model.fd_regulariser(xyzs, topo_w, perturb_noise, tr_['smoothness_std'], 1.0 / (3.0 * M_))
+                if self.world_size > 1 and not used_uniform:      # ragged shards: mean over the GLOBAL sample count
+                    l_np = l_np * (float(M_) / self._gcount(torch.tensor(float(M_), device=xyzs.device)))
+                results['loss_normal_perturb'] = l_np
+            else:
+                sdf, sigmas, rgbs, normals, deform, normal_raw = model(xyzs, time_step, light, ratio=ambient_ratio, shading=shading, cano=cano)
             weights, opacity, depth, rgb = nerfacc.composite(sigmas, rgbs, t_starts, t_ends, ray_indices, N, seg=seg)
             opacity = opacity[:, None]
             if bg_color is None:
@@ -308,7 +324,7 @@ class Renderer:
                 # `.sum(-1).mean()` on the [M] tensor (morpheus.py:712) is the SUM over all samples: a shard contributes
                 # world_size x its local sum, so that (loss / world_size) summed over the ranks is the global sum
                 results['loss_orient'] = (weights.detach() * (normals * t_dirs).sum(-1).clamp(min=0) ** 2).sum(-1).mean() * self.world_size
-            if tr['normal_smooth_3d'] > 0 and normals is not None:
+            if tr['normal_smooth_3d'] > 0 and normals is not None and 'loss_normal_perturb' not in results:
                 if tr.get('normal_dir', False) or not tr.get('topo_none', True):
                     raise NotImplementedError('normal_dir / topo_none=False branches are disabled in every shipped config')
                 if perturb_noise is None:

@@ -825,3 +825,66 @@ def test_edge_cases_empty_tiny_and_errors(dev):
                 assert rel_l2(cpu(a), cpu(b)) < 3e-4, M
     finally:
         _lib.USE_TC, _lib.USE_TC_BWD, _lib.USE_TC_BWD_SDF = old
+
+
+# ------------------------------------------------------------------------------------------------
+# fused FD-normal regulariser (csrc/field_fd_reg_tc.cu) -- morpheus.py:714-741 on a real view
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('M,max_level', [(1, 1.0), (17, 0.77), (130, 1.0), (1000 + 37, 0.77), (4096 + 5, 1.0)])
+def test_fd_regulariser_vs_fp64_oracle_and_general_path(dev, M, max_level):
+    """loss_normal_perturb = mean |normal(x, topo) - normal(x + noise * std, topo=None)|: the one-launch forward+backward kernel against
+    (a) the CPU oracle in float64 with autograd and (b) the library's general path (two `normal` queries + torch L1).  Points include the
+    AABB faces (clamped +-eps rows), exact cell centres / faces of the finest level and out-of-range samples; ragged M exercises partial
+    tiles, partial sub-tiles and (M = 4101) several tiles per CTA."""
+    from oracle.fields import SceneOracle, init_reference_like_state
+    sd = init_reference_like_state(200, seed=5, randomize=True, emb_scale=0.3)
+    g = torch.Generator().manual_seed(100 + M)
+    x = (torch.rand(M, 3, generator=g) * 2 - 1) * 1.0
+    if M >= 17:
+        x[0] = torch.tensor([1.01, -1.01, 0.3]); x[1] = torch.tensor([1.0095, 0.0, -1.0095])      # on / next to the AABB faces
+        x[2] = (torch.tensor([64.0, 17.0, 100.0]) / 128) * 2.02 - 1.01                           # exactly on cell faces of the finest level
+        x[3] = (torch.tensor([64.5, 17.5, 100.5]) / 128) * 2.02 - 1.01                           # exactly on cell centres
+        x[4] = torch.tensor([1.2, 0.1, 0.1])                                                      # outside the AABB (clamped rows)
+    topo = torch.randn(M, 2, generator=g) * 0.3
+    noise = torch.randn(M, 3, generator=g)
+    std = 0.005
+    # (a) fp64 oracle
+    sdo = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        sc = SceneOracle(sdo, 1.01, 200, max_level)
+        xo, to = x.double().requires_grad_(True), topo.double().requires_grad_(True)
+        n1, _ = sc.normal(xo, topo=to)
+        n2, _ = sc.normal(xo + noise.double() * std, topo=None)
+        lo = (n1 - n2).abs().mean()
+        lo.backward()
+    finally:
+        torch.set_default_dtype(prev)
+    # (b) general path
+    m = make_model(sd, max_level, dev).train()
+    xg, tg = x.to(dev).requires_grad_(True), topo.to(dev).requires_grad_(True)
+    a1, _ = m.normal(xg, topo=tg)
+    a2, _ = m.normal(xg + noise.to(dev) * std, topo=None)
+    lg = (a1 - a2).abs().mean()
+    lg.backward()
+    gen = {'x': xg.grad.clone(), 'topo': tg.grad.clone(), 'emb': m.encoder.embeddings.grad.clone(),
+           **{f'sdf{l}.{k}': getattr(m.sdf_net.net[l], k).grad.clone() for l in range(3) for k in ('weight', 'bias') if getattr(m.sdf_net.net[l], k).grad is not None}}
+    m.zero_grad()
+    # fused
+    xf, tf = x.to(dev).requires_grad_(True), topo.to(dev).requires_grad_(True)
+    lf, nf, rf = m.fd_regulariser(xf, tf, noise.to(dev), std, 1.0 / (3 * M))
+    (lf * 1.7).backward()                  # a non-unit upstream gradient: backward() only scales the stored gradients
+    fus = {'x': xf.grad / 1.7, 'topo': tf.grad / 1.7, 'emb': m.encoder.embeddings.grad / 1.7,
+           **{f'sdf{l}.{k}': getattr(m.sdf_net.net[l], k).grad / 1.7 for l in range(3) for k in ('weight', 'bias') if getattr(m.sdf_net.net[l], k).grad is not None}}
+    assert abs(float(lf) - float(lo)) <= 2e-5 * abs(float(lo)) + 1e-7, (float(lf), float(lo))
+    assert abs(float(lf) - float(lg)) <= 2e-5 * abs(float(lg)) + 1e-7, (float(lf), float(lg))
+    assert rel_l2(cpu(nf), cpu(a1)) < 1e-5 and rel_l2(cpu(nf), cpu(n1)) < 2e-3      # FD normals difference fp32 SDF values 4e-3 apart
+    ora = {'x': xo.grad, 'topo': to.grad, 'emb': sdo['encoder.embeddings'].grad,
+           **{f'sdf{l}.{k}': sdo[f'sdf_net.net.{l}.{k}'].grad for l in range(3) for k in ('weight', 'bias') if sdo[f'sdf_net.net.{l}.{k}'].grad is not None}}
+    errs_o = {k: rel_l2(cpu(fus[k]), cpu(ora[k])) for k in fus if k in ora and float(ora[k].abs().max()) > 0}
+    errs_g = {k: rel_l2(cpu(fus[k]), cpu(gen[k])) for k in fus if k in gen and float(gen[k].abs().max()) > 0}
+    floor = {k: rel_l2(cpu(gen[k]), cpu(ora[k])) for k in gen if k in ora and float(ora[k].abs().max()) > 0}
+    # bar: within 1e-3 of the exact (fp64) gradient, or at least as close to it as the general fp32 path
+    bad = {k: e for k, e in errs_o.items() if e > max(1e-3, 1.5 * floor.get(k, 0.0))}
+    assert len(errs_o) >= 7 and not bad, f'vs fp64 oracle: {bad}\nfused-vs-oracle {errs_o}\ngeneral-vs-oracle {floor}\nfused-vs-general {errs_g}'
