@@ -877,7 +877,8 @@ def test_fd_regulariser_vs_fp64_oracle_and_general_path(dev, M, max_level):
     (lf * 1.7).backward()                  # a non-unit upstream gradient: backward() only scales the stored gradients
     fus = {'x': xf.grad / 1.7, 'topo': tf.grad / 1.7, 'emb': m.encoder.embeddings.grad / 1.7,
            **{f'sdf{l}.{k}': getattr(m.sdf_net.net[l], k).grad / 1.7 for l in range(3) for k in ('weight', 'bias') if getattr(m.sdf_net.net[l], k).grad is not None}}
-    assert abs(float(lf) - float(lo)) <= 2e-5 * abs(float(lo)) + 1e-7, (float(lf), float(lo))
+    # (every FD normal differences fp32 SDF values 4e-3 apart: golden tolerance 2e-3 per normal)
+    assert abs(float(lf) - float(lo)) <= 2e-4 * abs(float(lo)) + 1e-7, (float(lf), float(lo))
     assert abs(float(lf) - float(lg)) <= 2e-5 * abs(float(lg)) + 1e-7, (float(lf), float(lg))
     assert rel_l2(cpu(nf), cpu(a1)) < 1e-5 and rel_l2(cpu(nf), cpu(n1)) < 2e-3      # FD normals difference fp32 SDF values 4e-3 apart
     ora = {'x': xo.grad, 'topo': to.grad, 'emb': sdo['encoder.embeddings'].grad,
