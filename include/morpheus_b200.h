@@ -193,6 +193,7 @@ int mb_field_backward_fd_tc(const mb_field_params* p, const mb_field_io* io, con
                             const uint32_t* tc_off, const void* tc_weights_t, const uint32_t* tc_off_t, int accumulate, mb_stream_t stream);
 /* debug: cumulative clock64 cycles per phase of mb_field_backward_fd_tc, summed over CTAs (16 host words); reset != 0 clears */
 int mb_debug_fd_phases(unsigned long long* host_out16, int reset);
+int mb_debug_fdr_phases(unsigned long long* host_out16, int reset);   /* same for mb_fd_regulariser_tc (build with -DMB_FDR_PHASE_TIMING=1) */
 /* Fused finite-difference normal regulariser of a real-view step: loss_normal_perturb of MorpheuS.render_rays (morpheus.py:714-741) =
  * mean |n(x, topo) - n(x + noise * noise_std, topo = 0)| with n = safe_normalize(6-point FD of the SDF, models/model.py:367-398), forward
  * AND backward in one launch (csrc/field_fd_reg_tc.cu).  Valid when the colour does not depend on the normal ('albedo_normal', ratio 1).

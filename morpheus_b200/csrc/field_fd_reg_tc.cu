@@ -42,6 +42,11 @@ constexpr int PITCH = RT * 16;          // bytes between 8-column core groups of
 constexpr int S0_LO = 10 * PITCH;       // lo offset of the 80-column S0 tile
 constexpr int X_LO = 8 * PITCH;         // lo offset of a 64-column tile (dZ)
 constexpr int X0_LO = 9 * PITCH;        // lo offset of the A1 tile: 64 columns + one core whose first column is the constant 1
+#ifndef MB_FDR_PHASE_TIMING
+#define MB_FDR_PHASE_TIMING 0           // 1: worker thread 0 accumulates clock64 deltas per phase (mb_debug_fdr_phases; a few % slower)
+#endif
+constexpr bool PHASE_TIMING = MB_FDR_PHASE_TIMING != 0;
+__device__ unsigned long long g_fdr_phase[16];
 
 struct Smem {
     static constexpr int S0 = 0;                          // 30720
@@ -54,10 +59,7 @@ struct Smem {
     static constexpr int STOPO = SPB + 3 * 512;           // [2][128]
     static constexpr int GACC = STOPO + 2 * 512;          // [3][128] d/dx
     static constexpr int GTOPO = GACC + 3 * 512;          // [2][128]
-    static constexpr int SPT = GTOPO + 2 * 512;           // [3][96] row-wise query points
-    static constexpr int GPT = SPT + 3 * 384;             // [3][96]
-    static constexpr int STQ = GPT + 3 * 384;             // [2][96]
-    static constexpr int PSUM = STQ + 2 * 384;            // [2][96] partial row-0 dot products (column halves)
+    static constexpr int PSUM = GTOPO + 2 * 512;          // [2][96] partial row-0 dot products (column halves)
     static constexpr int G0R = PSUM + 2 * 384;            // [96] d loss / d sdf per row (unscaled)
     static constexpr int CW2 = G0R + 384;                 // [64]  dW2[0, :] accumulator (scaled)
     static constexpr int MISC = CW2 + 256;                // 32 floats / ints of control state
@@ -72,6 +74,9 @@ static_assert(Smem::TOTAL <= 113 * 1024, "two CTAs per SM");
 enum { M_SCALE = 0, M_INV = 1, M_FLUSH = 2 /*int*/, M_FIRST = 3 /*int: wgrad MMAs of this sub-tile overwrite*/, M_OLDINV = 4, M_HAVE = 5 /*int*/,
        M_DIRTY = 6 /*int*/, M_LOSS = 7, M_GSUM = 8, M_MX = 16 /*[8]*/ };
 
+#ifdef MB_FDR_NO_RED
+#define red_add2(a, b, c) do { } while (0)
+#endif
 __device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -195,12 +200,11 @@ __device__ __forceinline__ void fd_gather(uint8_t* S0, int r0, int l, const Grid
     for (int q = 0; q < 6; q++) store_pair(S0, r0 + q, 40 + 2 * l, f[q].x, f[q].y, S0_LO, PITCH);
 }
 
-// backward of one row: blend weights -> corner accumulators (base / far plane), d/d(point) of the row (summed over the 16 levels of the
-// half-warp by shuffles; lane l == 0 adds it to gp)
+// backward of one row: blend weights -> corner accumulators (base / far plane); d/d(point) of the row, masked by the clamp derivative, is
+// added to the thread's running sum over the six rows
 template <int A, int SGN>
 __device__ __forceinline__ void scatter_row(const Stencil& st, const float2 (&cv)[8], const float2 (&ev)[4], float2 (&accb)[8], float2 (&acce)[4],
-                                            float g0, float g1, float res_f, float two_bound, float* __restrict__ gp, int row,
-                                            bool lane0) {
+                                            float g0, float g1, float res_f, float two_bound, const bool (&mk)[3], float (&dxsum)[3]) {
     float P[3] = {st.pos[0][0], st.pos[1][0], st.pos[2][0]};
     P[A] = st.pos[A][1 + SGN];
     const bool crossed = SGN == 0 ? st.cross[A] > 0 : st.cross[A] < 0;
@@ -212,21 +216,22 @@ __device__ __forceinline__ void scatter_row(const Stencil& st, const float2 (&cv
 #pragma unroll
         for (uint32_t d = 0; d < 3; d++) w = __fmul_rn(w, (k & (1u << d)) ? P[d] : __fsub_rn(1.0f, P[d]));
         const float a0 = w * g0, a1 = w * g1;
-        {
-            const bool bit = (k >> A) & 1;
-            const uint32_t j = compress<A>(k);
-            const bool far_side = SGN == 0 ? bit : !bit;                          // this corner lies on the far plane when the row crossed
-            const uint32_t kalt = SGN == 0 ? (k | (1u << A)) : (k & ~(1u << A));  // ... else it is this corner of the base cell
-            // static register indices only (k, kalt, j are compile-time after unrolling): three predicated accumulations
-            if (!crossed) { accb[k].x += a0; accb[k].y += a1; }
-            else if (far_side) { acce[j].x += a0; acce[j].y += a1; }
-            else { accb[kalt].x += a0; accb[kalt].y += a1; }
-        }
+        const bool bit = (k >> A) & 1;
+        const uint32_t j = compress<A>(k);
+        const bool far_side = SGN == 0 ? bit : !bit;                          // this corner lies on the far plane when the row crossed
+        const uint32_t kalt = SGN == 0 ? (k | (1u << A)) : (k & ~(1u << A));  // ... else it is this corner of the base cell
+        // static register indices only (k, kalt, j are compile-time after unrolling): three predicated accumulations
+        if (!crossed) { accb[k].x += a0; accb[k].y += a1; }
+        else if (far_side) { acce[j].x += a0; acce[j].y += a1; }
+        else { accb[kalt].x += a0; accb[kalt].y += a1; }
     }
-    float dx[3];
+    // h_k = <corner_k, g>: d f / d pos_d . g = sum over the 4 corner pairs along d of (bilinear weight of the other two axes) * (h_hi - h_lo)
+    float hk[8];
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) hk[k] = c[k].x * g0 + c[k].y * g1;
 #pragma unroll
     for (uint32_t gd = 0; gd < 3; gd++) {
-        float a = 0.f;
+        float acc = 0.f;
 #pragma unroll
         for (uint32_t i4 = 0; i4 < 4; i4++) {
             float w = res_f;
@@ -237,26 +242,16 @@ __device__ __forceinline__ void scatter_row(const Stencil& st, const float2 (&cv
                 if (i4 & (1u << nd)) { w *= P[d]; cl |= (1u << d); }
                 else w *= (1.0f - P[d]);
             }
-            const float2 lo = c[cl], hi = c[cl | (1u << gd)];
-            a += w * ((hi.x - lo.x) * g0 + (hi.y - lo.y) * g1);
+            acc += w * (hk[cl | (1u << gd)] - hk[cl]);
         }
-        dx[gd] = a / two_bound;
-    }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-#pragma unroll
-        for (int d = 0; d < 3; d++) dx[d] += __shfl_xor_sync(0xffffffffu, dx[d], o);
-    }
-    if (lane0) {
-#pragma unroll
-        for (int d = 0; d < 3; d++) gp[d * RT + row] += dx[d];
+        if (mk[gd]) dxsum[gd] += acc / two_bound;
     }
 }
 
 template <int A>
 __device__ __forceinline__ void scatter_axis(const Stencil& st, const LevelInfo& L, const float2* __restrict__ tab, float* __restrict__ gt,
                                              const float2 (&cv)[8], float2 (&accb)[8], const float* __restrict__ G, int r0, int l, float inv_scale,
-                                             float two_bound, float* __restrict__ gp, bool live, bool lane0) {
+                                             float two_bound, bool live, const bool (&mb_)[3], bool mplus, bool mminus, float (&dxsum)[3]) {
     float2 ev[4], acce[4];
 #pragma unroll
     for (uint32_t j = 0; j < 4; j++) {
@@ -264,15 +259,18 @@ __device__ __forceinline__ void scatter_axis(const Stencil& st, const LevelInfo&
         acce[j] = make_float2(0.f, 0.f);
     }
     const float res_f = (float)L.res;
+    bool mk[3] = {mb_[0], mb_[1], mb_[2]};
     {
         const int r = r0 + 2 * A;
         const float g0 = live ? G[(2 * l) * RT + r] * inv_scale : 0.f, g1 = live ? G[(2 * l + 1) * RT + r] * inv_scale : 0.f;
-        scatter_row<A, 0>(st, cv, ev, accb, acce, g0, g1, res_f, two_bound, gp, r, lane0);
+        mk[A] = mplus;
+        scatter_row<A, 0>(st, cv, ev, accb, acce, g0, g1, res_f, two_bound, mk, dxsum);
     }
     {
         const int r = r0 + 2 * A + 1;
         const float g0 = live ? G[(2 * l) * RT + r] * inv_scale : 0.f, g1 = live ? G[(2 * l + 1) * RT + r] * inv_scale : 0.f;
-        scatter_row<A, 1>(st, cv, ev, accb, acce, g0, g1, res_f, two_bound, gp, r, lane0);
+        mk[A] = mminus;
+        scatter_row<A, 1>(st, cv, ev, accb, acce, g0, g1, res_f, two_bound, mk, dxsum);
     }
     if (live && st.cross[A]) {
 #pragma unroll
@@ -280,40 +278,78 @@ __device__ __forceinline__ void scatter_axis(const Stencil& st, const LevelInfo&
     }
 }
 
-// hash-grid backward of one sub-tile: thread = (sample, set, level); G[32][RT] = feature gradients of the 96 rows (scaled)
-__device__ __noinline__ void fd_scatter(const GridCtx g, const float* __restrict__ spt_base /* [3][2*SS] clamped base points */,
-                                        const float* __restrict__ spt, const float* __restrict__ G, float* __restrict__ gemb, float* __restrict__ gp,
-                                        float inv_scale, int tid) {
-    const int l = tid & 15, pr = tid >> 4;          // pr = sample * 2 + set
+// the (clamped) query points of one (sample, set): base, +eps and -eps per axis; inb* = clamp derivative (1 where the clamp is inactive)
+struct PairPoints { float cb[3], pp[3], pm[3]; bool inb[3], inp[3], inm[3]; };
+__device__ __forceinline__ void pair_points(PairPoints& q, const float* __restrict__ base, int s, float bound) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const float v = base[d * TM + s], vp = __fadd_rn(v, FD_EPS), vm = __fadd_rn(v, -FD_EPS);
+        q.cb[d] = fminf(fmaxf(v, -bound), bound);
+        q.pp[d] = fminf(fmaxf(vp, -bound), bound);
+        q.pm[d] = fminf(fmaxf(vm, -bound), bound);
+        q.inb[d] = v >= -bound && v <= bound;
+        q.inp[d] = vp >= -bound && vp <= bound;
+        q.inm[d] = vm >= -bound && vm <= bound;
+    }
+}
+
+// hash-grid backward of one sub-tile.  Thread = (level, pair) with the 16 (sample, set) pairs of one level in the 16 lanes of a half-warp:
+// neighbouring pairs (the two sets of a sample, consecutive samples of a ray) that share the base cell are merged by a segmented
+// shuffle reduction before the red.v2 (the table scatter is bound by the LSU's atomic issue rate); d/d(point), summed over the six rows
+// and the 16 levels, goes to gacc [3][TM] (shared-memory atomics).  G[32][RT] = feature gradients of the 96 rows (scaled).
+__device__ __noinline__ void fd_scatter(const GridCtx g, const float* __restrict__ base, int s, const float* __restrict__ G, float* __restrict__ gemb,
+                                        float* __restrict__ gacc, float inv_scale, int tid) {
+    const int l = (tid >> 4) & 15, pr = tid & 15, lane = tid & 31, l16 = lane & 15;
     const int r0 = pr * 6;
     const bool live = (uint32_t)l < g.n_levels;
     const LevelInfo L = g.lv[live ? l : 0];
     const float2* tab = reinterpret_cast<const float2*>(g.emb) + L.off;
     float* gt = gemb + 2 * (size_t)L.off;
-    float cb[3], pp[3], pm[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        cb[d] = spt_base[d * (2 * SS) + pr];
-        pp[d] = spt[d * RT + r0 + 2 * d];           // row 2d   = +eps along axis d (clamped)
-        pm[d] = spt[d * RT + r0 + 2 * d + 1];       // row 2d+1 = -eps along axis d
-    }
+    PairPoints q;
+    pair_points(q, base, s, g.bound);
     Stencil st;
-    stencil_setup(st, g, L.res, cb, pp, pm);
+    stencil_setup(st, g, L.res, q.cb, q.pp, q.pm);
     float2 cv[8], accb[8];
 #pragma unroll
     for (uint32_t c = 0; c < 8; c++) {
         cv[c] = live ? __ldg(tab + base_index(st, L, c)) : make_float2(0.f, 0.f);
         accb[c] = make_float2(0.f, 0.f);
     }
-    const bool lane0 = l == 0;
-    scatter_axis<0>(st, L, tab, gt, cv, accb, G, r0, l, inv_scale, g.two_bound, gp, live, lane0);
-    scatter_axis<1>(st, L, tab, gt, cv, accb, G, r0, l, inv_scale, g.two_bound, gp, live, lane0);
-    scatter_axis<2>(st, L, tab, gt, cv, accb, G, r0, l, inv_scale, g.two_bound, gp, live, lane0);
-    if (live) {
+    float dxsum[3] = {0.f, 0.f, 0.f};
+    scatter_axis<0>(st, L, tab, gt, cv, accb, G, r0, l, inv_scale, g.two_bound, live, q.inb, q.inp[0], q.inm[0], dxsum);
+    scatter_axis<1>(st, L, tab, gt, cv, accb, G, r0, l, inv_scale, g.two_bound, live, q.inb, q.inp[1], q.inm[1], dxsum);
+    scatter_axis<2>(st, L, tab, gt, cv, accb, G, r0, l, inv_scale, g.two_bound, live, q.inb, q.inp[2], q.inm[2], dxsum);
+    // ---- merge runs of equal base cells among the 16 pairs of this level (segmented reduction towards the run head) ----
+    const uint32_t key = live ? (st.pg[0] | (st.pg[1] << 8) | (st.pg[2] << 16)) : (0x80000000u | (uint32_t)lane);
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1, 16);
+    const bool head = l16 == 0 || key != prev;
+    const uint32_t heads = (__ballot_sync(0xffffffffu, head) >> (lane & 16)) & 0xFFFFu;
+    const uint32_t after = heads >> (l16 + 1);
+    const int rem = after ? __ffs(after) : 16 - l16;          // lanes l16 .. l16 + rem - 1 belong to this lane's run
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+        const bool take = d < rem;
+#pragma unroll
+        for (uint32_t c = 0; c < 8; c++) {
+            const float vx = __shfl_down_sync(0xffffffffu, accb[c].x, d, 16), vy = __shfl_down_sync(0xffffffffu, accb[c].y, d, 16);
+            if (take) { accb[c].x += vx; accb[c].y += vy; }
+        }
+    }
+    if (live && head) {
 #pragma unroll
         for (uint32_t c = 0; c < 8; c++) {
             if (accb[c].x != 0.f || accb[c].y != 0.f) red_add2(gt + 2 * base_index(st, L, c), accb[c].x, accb[c].y);
         }
+    }
+    // ---- d/d(sample point): sum over the two sets (lane bit 0) and the two levels of the warp (lane bit 4), then shared-memory atomics ----
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        dxsum[d] += __shfl_xor_sync(0xffffffffu, dxsum[d], 1);
+        dxsum[d] += __shfl_xor_sync(0xffffffffu, dxsum[d], 16);
+    }
+    if ((lane & 17) == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) atomicAdd(gacc + d * TM + s, dxsum[d]);
     }
 }
 
@@ -342,9 +378,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) fd_reg_tc_kernel(const mb_field_p
     float* stopo = reinterpret_cast<float*>(smem + Smem::STOPO);
     float* gacc = reinterpret_cast<float*>(smem + Smem::GACC);
     float* gtopo = reinterpret_cast<float*>(smem + Smem::GTOPO);
-    float* spt = reinterpret_cast<float*>(smem + Smem::SPT);
-    float* gpt = reinterpret_cast<float*>(smem + Smem::GPT);
-    float* stq = reinterpret_cast<float*>(smem + Smem::STQ);
     float* psum = reinterpret_cast<float*>(smem + Smem::PSUM);
     float* g0r = reinterpret_cast<float*>(smem + Smem::G0R);
     float* cw2 = reinterpret_cast<float*>(smem + Smem::CW2);
@@ -357,7 +390,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) fd_reg_tc_kernel(const mb_field_p
     uint64_t* empty = bars + NSTAGE;
     uint64_t* acc_ready = bars + 2 * NSTAGE;
     uint64_t* z_ready = bars + 2 * NSTAGE + 1;
-    __shared__ float s_base[3 * 2 * SS];        // clamped base point of every (sample, set) of the sub-tile
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* AR = p.arena;
@@ -502,6 +534,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) fd_reg_tc_kernel(const mb_field_p
             store_core(X0, tid, 8, one8, X0_LO, PITCH);
         }
         const float b2 = __ldg(AR + p.sdf[2].b_off);
+        unsigned long long ph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        long long tprev = clock64();
+#define FDR_PHASE(i) do { if (PHASE_TIMING && tid == 0) { const long long tn = clock64(); ph[i] += (unsigned long long)(tn - tprev); tprev = tn; } } while (0)
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const uint32_t m0 = tile * TMt;
             const int nv = (int)min(TMt, a.M - m0);
@@ -527,56 +562,43 @@ __global__ void __launch_bounds__(NTHREADS, 2) fd_reg_tc_kernel(const mb_field_p
                 misc[M_SCALE] = 1.f; misc[M_INV] = 1.f; misci[M_HAVE] = 0; misci[M_DIRTY] = 0; misc[M_LOSS] = 0.f; misc[M_GSUM] = 0.f;
             }
             bar_workers();
+            FDR_PHASE(0);
 
 #pragma unroll 1
             for (int j = 0; j < nsub; j++) {
-                // ---- rows of the sub-tile: r = 12 sl + 6 set + q ; sample s = 8 j + sl ----
-                if (tid < RT) {
-                    const int sl = tid / 12, rem = tid - sl * 12, set = rem / 6, qq = rem - set * 6;
-                    const int s = SS * j + sl;
-                    const int axis = qq >> 1;
-                    const float e = (qq & 1) ? -FD_EPS : FD_EPS;
-                    const float* base = set ? spb : spa;
-#pragma unroll
-                    for (int ax = 0; ax < 3; ax++) {
-                        float v = base[ax * TM + s];
-                        if (ax == axis) v = __fadd_rn(v, e);
-                        spt[ax * RT + tid] = fminf(fmaxf(v, -p.bound), p.bound);
-                        gpt[ax * RT + tid] = 0.f;
-                    }
-                    stq[tid] = set ? 0.f : stopo[s];
-                    stq[RT + tid] = set ? 0.f : stopo[TM + s];
-                } else if (tid < RT + 3 * 2 * SS) {
-                    const int i = tid - RT, ax = i / (2 * SS), pr = i - ax * (2 * SS);
-                    const int s = SS * j + (pr >> 1);
-                    const float v = ((pr & 1) ? spb : spa)[ax * TM + s];
-                    s_base[ax * (2 * SS) + pr] = fminf(fmaxf(v, -p.bound), p.bound);
-                }
-                bar_workers();
-                // ---- S0: hash-grid features (thread = sample x set x level, shared corners) + frequency features + pads ----
+                // ---- rows of the sub-tile: r = 6 pr + q, pair pr = 2 sl + set, sample s = 8 j + sl.  No staging of the row points: every
+                //      consumer derives them from the sample points (a few FADD / FMNMX), which saves a barrier per sub-tile ----
+                FDR_PHASE(1);
+                // ---- S0: hash-grid features (thread = level x pair, shared corners; the 16 pairs of a level sit in one half-warp, so
+                //      pairs in the same cell coalesce into the same sectors) ----
                 {
-                    const int l = tid & 15, pr = tid >> 4, r0 = pr * 6;
-                    float cb[3], pp[3], pm[3];
-#pragma unroll
-                    for (int d = 0; d < 3; d++) {
-                        cb[d] = s_base[d * (2 * SS) + pr];
-                        pp[d] = spt[d * RT + r0 + 2 * d];
-                        pm[d] = spt[d * RT + r0 + 2 * d + 1];
-                    }
-                    fd_gather(S0, r0, l, gs, cb, pp, pm);
+                    const int l = tid >> 4, pr = tid & 15;
+                    const int s = SS * j + (pr >> 1);
+                    PairPoints q;
+                    pair_points(q, (pr & 1) ? spb : spa, s, p.bound);
+                    fd_gather(S0, pr * 6, l, gs, q.cb, q.pp, q.pm);
                 }
+                FDR_PHASE(2);
+                // ---- S0: frequency features (3 axes x 96 rows) + pads.  (Sharing the sin / cos of the coordinates the six rows of a pair have in
+                //      common was tried: the fp16 (hi, lo) conversions and 2-byte stores dominate this phase, not the sincosf -- slower.) ----
                 for (int it = tid; it < 4 * RT; it += NWORK) {
                     const int r = it % RT, ax = it / RT;
+                    const int pr = r / 6, qq = r - pr * 6;
+                    const int s = SS * j + (pr >> 1);
                     if (ax < 3) {
-                        freq_axis_tc(S0, r, ax, spt[ax * RT + r], (int)p.n_freq, S0_LO, PITCH);
+                        float v = ((pr & 1) ? spb : spa)[ax * TM + s];
+                        if (ax == (qq >> 1)) v = __fadd_rn(v, (qq & 1) ? -FD_EPS : FD_EPS);
+                        freq_axis_tc(S0, r, ax, fminf(fmaxf(v, -p.bound), p.bound), (int)p.n_freq, S0_LO, PITCH);
                     } else {
                         store_one(S0, r, 39, 1.0f, S0_LO, PITCH);      // constant-1 pad feature (its W0 column is zero): db0 from the wgrad MMA
-                        const float v[8] = {stq[r], stq[RT + r], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        const float v[8] = {(pr & 1) ? 0.f : stopo[s], (pr & 1) ? 0.f : stopo[TM + s], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                         store_core(S0, r, 9, v, S0_LO, PITCH);
                     }
                 }
+                FDR_PHASE(3);
                 // ---- A1 = relu(S0 W0^T + b0) -> X0 ----
                 signal_z(); wait_acc();
+                FDR_PHASE(4);
                 if (erow) {
                     float v[32];
                     tmem_ld32(tmem + lane_base + h * 32, v);
@@ -589,8 +611,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) fd_reg_tc_kernel(const mb_field_p
                         store_core(X0, m, h * 4 + c, o, X0_LO, PITCH);
                     }
                 }
+                FDR_PHASE(5);
                 // ---- Z2 = A1 W1^T (+ b1): pass 1 = sdf of the row (dot product with W2[0, :]); the accumulator stays in TMEM ----
                 signal_z(); wait_acc();
+                FDR_PHASE(6);
                 if (erow) {
                     float v[32];
                     tmem_ld32(tmem + lane_base + h * 32, v);
@@ -602,6 +626,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) fd_reg_tc_kernel(const mb_field_p
                     psum[h * RT + m] = acc;
                 }
                 bar_workers();
+                FDR_PHASE(7);
                 // ---- normals of both sets, loss, d loss / d sdf of the 12 rows of a sample (8 threads), scale control (thread 0) ----
                 if (warp == 0) {
                     float mx = 0.f;
@@ -695,6 +720,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) fd_reg_tc_kernel(const mb_field_p
                     bar_workers();
                 }
                 const float scale = misc[M_SCALE], inv_scale = misc[M_INV];
+                FDR_PHASE(8);
                 // ---- pass 2: dZ1 = g0 W2[0,:] (A2 > 0) -> DZ ; dW2[0,:] += g0 A2 ----
                 {
                     float z[32], ga[32];
@@ -721,8 +747,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) fd_reg_tc_kernel(const mb_field_p
                         atomicAdd(cw2 + h * 32 + lane, cg);
                     }
                 }
+                FDR_PHASE(9);
                 // ---- dZ0 = (dZ1 W1) (A1 > 0) -> DZ ----
                 signal_z(); wait_acc();
+                FDR_PHASE(10);
                 if (erow) {
                     float v[32];
                     tmem_ld32(tmem + lane_base + h * 32, v);
@@ -741,32 +769,49 @@ __global__ void __launch_bounds__(NTHREADS, 2) fd_reg_tc_kernel(const mb_field_p
                         store_core(DZ, m, kc, o, X_LO, PITCH);
                     }
                 }
+                FDR_PHASE(11);
                 // ---- d(S0) (80 columns): h = 0: frequency columns 0..38 -> sin/cos backward ; h = 1: grid columns 40..71 -> G, topo 72..73 ----
                 signal_z(); wait_acc();
+                FDR_PHASE(12);
                 if (erow) {
+                    const int pr = m / 6, qq = m - pr * 6;
+                    const int s = SS * j + (pr >> 1);
                     if (h == 0) {
+                        // frequency path: d/d(point) = g_x + sum_k 2^k (g_sin cos - g_cos sin).  The sin / cos VALUES are the forward features,
+                        // still in the S0 operand tile as fp16 (hi, lo) pairs (exact to 2^-22): no second sincosf
                         float v[32], w[8];
                         tmem_ld32(tmem + lane_base, v);
                         tmem_ld8(tmem + lane_base + 32, w);
-                        float f = 1.0f;
                         float acc3[3] = {v[0], v[1], v[2]};
+                        const uint8_t* srow = S0 + (m >> 3) * 128 + (m & 7) * 16;
 #pragma unroll
-                        for (int k = 0; k < 6; k++) {
-                            if (k < (int)p.n_freq) {
+                        for (int c = 0; c < 5; c++) {
+                            const uint4 hi = *reinterpret_cast<const uint4*>(srow + c * PITCH);
+                            const uint4 lo = *reinterpret_cast<const uint4*>(srow + c * PITCH + S0_LO);
+                            const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
-                                for (int ax = 0; ax < 3; ax++) {
-                                    float sn, cn;
-                                    sincosf(spt[ax * RT + m] * f, &sn, &cn);
-                                    const int is = 3 + 6 * k + ax, ic = 6 + 6 * k + ax;
-                                    const float gs_ = is < 32 ? v[is] : w[is - 32];
-                                    const float gc_ = ic < 32 ? v[ic] : w[ic - 32];
-                                    acc3[ax] += f * (gs_ * cn - gc_ * sn);
+                            for (int i = 0; i < 8; i++) {
+                                const int fi = c * 8 + i;
+                                if (fi >= 3 && fi < 39) {
+                                    const int kk = (fi - 3) / 6, t = (fi - 3) - kk * 6;       // t < 3: sin of axis t ; else cos of axis t - 3
+                                    const __half hv = __ushort_as_half((unsigned short)(hw[i >> 1] >> ((i & 1) * 16)));
+                                    const __half lv = __ushort_as_half((unsigned short)(lw[i >> 1] >> ((i & 1) * 16)));
+                                    const float val = __half2float(hv) + __half2float(lv);
+                                    const float fr = (float)(1 << kk);
+                                    if (kk < (int)p.n_freq) {
+                                        if (t < 3) { const int ic = fi + 3; acc3[t] -= fr * (ic < 32 ? v[ic] : w[ic - 32]) * val; }
+                                        else { const int is = fi - 3; acc3[t - 3] += fr * (is < 32 ? v[is] : w[is - 32]) * val; }
+                                    }
                                 }
                             }
-                            f *= 2.0f;
                         }
+                        const float* base = (pr & 1) ? spb : spa;
 #pragma unroll
-                        for (int ax = 0; ax < 3; ax++) atomicAdd(gpt + ax * RT + m, acc3[ax] * inv_scale);
+                        for (int ax = 0; ax < 3; ax++) {
+                            float pv = base[ax * TM + s];
+                            if (ax == (qq >> 1)) pv = __fadd_rn(pv, (qq & 1) ? -FD_EPS : FD_EPS);
+                            if (pv >= -p.bound && pv <= p.bound) atomicAdd(gacc + ax * TM + s, acc3[ax] * inv_scale);      // clamp derivative
+                        }
                     } else {
                         // G aliases DZ: the MMAs that read DZ completed before acc_ready fired
                         float v[32], t4[4];
@@ -774,9 +819,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) fd_reg_tc_kernel(const mb_field_p
                         tmem_ld4(tmem + lane_base + 72, t4);
 #pragma unroll
                         for (int i = 0; i < 32; i++) G[i * RT + m] = v[i];
-                        const int sl = m / 12, set = (m - sl * 12) / 6;
-                        if (a.topo && set == 0) {
-                            const int s = SS * j + sl;
+                        if (a.topo && (pr & 1) == 0) {
                             atomicAdd(gtopo + s, t4[0] * inv_scale);
                             atomicAdd(gtopo + TM + s, t4[1] * inv_scale);
                         }
@@ -784,24 +827,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) fd_reg_tc_kernel(const mb_field_p
                 }
                 tc_fence_before();
                 bar_workers();
-                fd_scatter(gs, s_base, spt, G, a.g_emb, gpt, inv_scale, tid);
-                bar_workers();
-                // ---- fold the row gradients into the sample gradients (clamp derivative) ----
-                if (tid < RT) {
-                    const int sl = tid / 12, rem = tid - sl * 12, set = rem / 6, qq = rem - set * 6;
-                    const int s = SS * j + sl;
-                    const int axis = qq >> 1;
-                    const float e = (qq & 1) ? -FD_EPS : FD_EPS;
-                    const float* base = set ? spb : spa;
-#pragma unroll
-                    for (int ax = 0; ax < 3; ax++) {
-                        float v = base[ax * TM + s];
-                        if (ax == axis) v = __fadd_rn(v, e);
-                        if (v >= -p.bound && v <= p.bound) atomicAdd(gacc + ax * TM + s, gpt[ax * RT + tid]);
-                    }
+                FDR_PHASE(13);
+                {
+                    const int pr = tid & 15;
+                    fd_scatter(gs, (pr & 1) ? spb : spa, SS * j + (pr >> 1), G, a.g_emb, gacc, inv_scale, tid);
                 }
+                bar_workers();          // G (aliasing DZ) and S0 are rewritten by the next sub-tile
+                FDR_PHASE(14);
             }
 
+            FDR_PHASE(15);
             // ---- end of tile: flush the accumulators, loss, per-sample gradients ----
             bar_workers();
             flush(misc[M_INV]);
@@ -819,6 +854,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) fd_reg_tc_kernel(const mb_field_p
             }
             bar_workers();
         }
+        if (PHASE_TIMING && tid == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) atomicAdd(&g_fdr_phase[i], ph[i]);
+        }
+#undef FDR_PHASE
     }
     tc_fence_before();
     __syncthreads();
@@ -858,4 +898,13 @@ extern "C" int mb_fd_regulariser_tc(const mb_field_params* p, const float* x, co
     tcr::fd_reg_tc_kernel<<<grid, tcr::NTHREADS, smem, (cudaStream_t)stream>>>(*p, a, (const uint8_t*)tc_weights, tc_off, (const uint8_t*)tc_weights_t,
                                                                               tc_off_t, nsub);
     return check_launch("fd_regulariser_tc");
+}
+
+/* debug: cumulative clock64 cycles per phase of mb_fd_regulariser_tc (worker thread 0 of every CTA; needs -DMB_FDR_PHASE_TIMING=1) */
+extern "C" int mb_debug_fdr_phases(unsigned long long* host_out16, int reset) {
+    using namespace mb;
+    unsigned long long z[16] = {0};
+    if (host_out16 && cudaMemcpyFromSymbol(host_out16, tcr::g_fdr_phase, sizeof(z)) != cudaSuccess) { set_error("debug_fdr_phases: copy failed"); return MB_ECUDA; }
+    if (reset && cudaMemcpyToSymbol(tcr::g_fdr_phase, z, sizeof(z)) != cudaSuccess) { set_error("debug_fdr_phases: reset failed"); return MB_ECUDA; }
+    return MB_OK;
 }

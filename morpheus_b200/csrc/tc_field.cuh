@@ -69,11 +69,12 @@ __device__ __forceinline__ void store_one(uint8_t* A, int m, int k, float f, int
     *reinterpret_cast<__half*>(p + lo_off) = l;
 }
 __device__ __forceinline__ void store_pair(uint8_t* A, int m, int k, float f0, float f1, int lo_off = A_LO_OFF, int pitch = 2048) {
-    const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
-    const __half l0 = __float2half_rn(f0 - __half2float(h0)), l1 = __float2half_rn(f1 - __half2float(h1));
+    const __half2 hh = __floats2half2_rn(f0, f1);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
     uint8_t* p = A + (k >> 3) * pitch + (m >> 3) * 128 + (m & 7) * 16 + (k & 7) * 2;
-    *reinterpret_cast<uint32_t*>(p) = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    *reinterpret_cast<uint32_t*>(p + lo_off) = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<const uint32_t*>(&hh);
+    *reinterpret_cast<uint32_t*>(p + lo_off) = *reinterpret_cast<const uint32_t*>(&ll);
 }
 // frequency features of ONE axis a of point coordinate v: tc columns a, 3+6k+a (sin), 6+6k+a (cos)
 __device__ __forceinline__ void freq_axis_tc(uint8_t* A, int m, int a, float v, int n_freq, int lo_off = A_LO_OFF, int pitch = 2048) {
