@@ -240,6 +240,16 @@ int mb_sds_grad(const float* eps_uncond, const float* eps_cond, const float* noi
 int mb_add_noise(const float* z, const float* eps, float sqrt_abar, float sqrt_one_minus_abar, float* out, uint32_t n,
                  mb_stream_t stream);
 
+/* device-scalar variants (no host synchronisation, CUDA-graph capturable): t_dev = the diffusion step (int64 [1] on the device),
+ * alphas_cumprod [1000] on the device; latents_noisy = sqrt(abar_t) z + sqrt(1 - abar_t) eps  (DDIMScheduler.add_noise, zero123_utils.py:180) */
+int mb_add_noise_dev(const float* z, const float* eps, const float* alphas_cumprod, const int64_t* t_dev, float* out, uint32_t n,
+                     mb_stream_t stream);
+/* grad (+)= view_weight * grad_scale_dev[0] * (1 - abar_t) * (eps_u + s (eps_c - eps_u) - eps)   (zero123_utils.py:204-212; the caller applies
+ * nan_to_num once after the weighted sum over the reference views) */
+int mb_sds_grad_dev(const float* eps_uncond, const float* eps_cond, const float* noise, float guidance_scale, const float* grad_scale_dev,
+                    const float* alphas_cumprod, const int64_t* t_dev, float view_weight, float* grad, uint32_t n, int accumulate,
+                    mb_stream_t stream);
+
 /* ---- (8) host-glue kernels of the step (each replaces tens to hundreds of eager launches) ------------------------- */
 /* xyz[i] = rays_o[ray_indices[i]] + rays_d[ray_indices[i]] * (t_starts[i]+t_ends[i])/2        morpheus.py:645-646 */
 int mb_ray_points_forward(const float* rays_o, const float* rays_d, const int64_t* ray_indices, const float* t_starts,

@@ -188,6 +188,27 @@ __global__ void add_noise_kernel(const float* __restrict__ z, const float* __res
     if (i < n) out[i] = a * z[i] + b * e[i];
 }
 
+// device-scalar variants of the SDS chain: t, abar_t and the per-step weights stay on the device, so Zero123.train_step has no
+// device->host synchronisation and the whole chain (VAE encode, add-noise, UNet, gradient, VAE input-gradient) is ONE CUDA graph
+__global__ void add_noise_dev_kernel(const float* __restrict__ z, const float* __restrict__ e, const float* __restrict__ alphas_cumprod,
+                                     const int64_t* __restrict__ t, float* __restrict__ out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float ab = alphas_cumprod[t[0]];
+    out[i] = sqrtf(ab) * z[i] + sqrtf(1.0f - ab) * e[i];
+}
+__global__ void sds_grad_dev_kernel(const float* __restrict__ eu, const float* __restrict__ ec, const float* __restrict__ noise, float s,
+                                    const float* __restrict__ grad_scale, const float* __restrict__ alphas_cumprod, const int64_t* __restrict__ t,
+                                    float view_weight, float* __restrict__ grad, uint32_t n, int accumulate) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float wg = grad_scale[0] * (1.0f - alphas_cumprod[t[0]]);       // grad_scale * w(t), w = 1 - abar_t (zero123_utils.py:210)
+    const float pred = eu[i] + s * (ec[i] - eu[i]);
+    float g = view_weight * (wg * (pred - noise[i]));
+    if (accumulate) g += grad[i];
+    grad[i] = g;
+}
+
 }  // namespace mb
 
 using namespace mb;
@@ -287,6 +308,24 @@ extern "C" int mb_sds_grad(const float* eps_uncond, const float* eps_cond, const
     if (!eps_uncond || !eps_cond || !noise || !grad) { set_error("sds_grad: null pointer"); return MB_EINVAL; }
     sds_grad_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(eps_uncond, eps_cond, noise, guidance_scale, w_t_times_grad_scale, grad, n);
     return check_launch("sds_grad");
+}
+
+extern "C" int mb_add_noise_dev(const float* z, const float* eps, const float* alphas_cumprod, const int64_t* t_dev, float* out, uint32_t n,
+                                mb_stream_t stream) {
+    if (n == 0) return MB_OK;
+    if (!z || !eps || !alphas_cumprod || !t_dev || !out) { set_error("add_noise_dev: null pointer"); return MB_EINVAL; }
+    add_noise_dev_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(z, eps, alphas_cumprod, t_dev, out, n);
+    return check_launch("add_noise_dev");
+}
+
+extern "C" int mb_sds_grad_dev(const float* eps_uncond, const float* eps_cond, const float* noise, float guidance_scale, const float* grad_scale_dev,
+                               const float* alphas_cumprod, const int64_t* t_dev, float view_weight, float* grad, uint32_t n, int accumulate,
+                               mb_stream_t stream) {
+    if (n == 0) return MB_OK;
+    if (!eps_uncond || !eps_cond || !noise || !grad_scale_dev || !alphas_cumprod || !t_dev || !grad) { set_error("sds_grad_dev: null pointer"); return MB_EINVAL; }
+    sds_grad_dev_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(eps_uncond, eps_cond, noise, guidance_scale, grad_scale_dev, alphas_cumprod,
+                                                                        t_dev, view_weight, grad, n, accumulate);
+    return check_launch("sds_grad_dev");
 }
 
 extern "C" int mb_add_noise(const float* z, const float* eps, float sqrt_abar, float sqrt_one_minus_abar, float* out, uint32_t n,

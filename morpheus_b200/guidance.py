@@ -239,6 +239,8 @@ class Zero123(torch.nn.Module):
         self.precision = precision
         self.graph = graph
         self._graph = None
+        self._chain = {}
+        self._in_chain = False
 
     def update_t_range(self, t_range):
         self.t_range = t_range
@@ -277,16 +279,17 @@ class Zero123(torch.nn.Module):
 
     # -- the UNet leg: noise prediction with classifier-free guidance -> SDS gradient -------------------------------
     @torch.no_grad()
-    def sds_grad(self, latents, noise, t, c_crossattn, c_concat, T, guidance_scale, grad_scale_w):
-        """zero123_utils.py:177-212 for one reference view: add_noise -> UNet(x2, CFG) -> grad_scale*w(t)*(eps_hat - eps).
-        t: LongTensor [1]; grad_scale_w: 0-dim/[1] tensor = grad_scale * (1 - abar_t)."""
+    def sds_grad(self, latents, noise, t, c_crossattn, c_concat, T, guidance_scale, grad_scale_dev, view_weight=1.0, out=None, accumulate=False):
+        """zero123_utils.py:177-212 for one reference view: add_noise -> UNet(x2, CFG) -> view_weight * grad_scale * w(t) * (eps_hat - eps),
+        written (or accumulated) into `out`.  t: LongTensor [1] ON THE DEVICE; grad_scale_dev: float tensor [1] on the device.  No
+        device->host synchronisation: abar_t and w(t) = 1 - abar_t are looked up by the kernels (mb_add_noise_dev, mb_sds_grad_dev)."""
         L = _lib.lib()
         lat = latents.detach().contiguous().float()
         noise = noise.contiguous().float()
-        ab = self.alphas[t].reshape(())
+        t = t.reshape(-1)[:1].contiguous().long()
+        gs = grad_scale_dev.reshape(-1)[:1].contiguous().float()
         noisy = torch.empty_like(lat)
-        check(L.mb_add_noise(ptr(lat), ptr(noise), _lib.C.c_float(float(ab.sqrt())), _lib.C.c_float(float((1 - ab).sqrt())), ptr(noisy),
-                             lat.numel(), stream()), 'add_noise')
+        check(L.mb_add_noise_dev(ptr(lat), ptr(noise), ptr(self.alphas), ptr(t), ptr(noisy), lat.numel(), stream()), 'add_noise_dev')
         clip_emb = F.linear(torch.cat([c_crossattn, T], dim=-1), self.cc['weight'], self.cc['bias'])       # ddpm.py:526 Linear(772, 768)
         ctx = torch.cat([torch.zeros_like(clip_emb), clip_emb], dim=0)                                       # [2,1,768]
         cc = torch.cat([torch.zeros_like(c_concat), c_concat], dim=0)                                        # [2,4,32,32]
@@ -294,9 +297,9 @@ class Zero123(torch.nn.Module):
         t_in = torch.cat([t] * 2)
         eps = self._unet(x_in, t_in, ctx)
         eu, ec = eps[0:1].contiguous(), eps[1:2].contiguous()
-        grad = torch.empty_like(lat)
-        check(L.mb_sds_grad(ptr(eu), ptr(ec), ptr(noise), _lib.C.c_float(float(guidance_scale)), _lib.C.c_float(float(grad_scale_w)),
-                            ptr(grad), lat.numel(), stream()), 'sds_grad')
+        grad = out if out is not None else torch.empty_like(lat)
+        check(L.mb_sds_grad_dev(ptr(eu), ptr(ec), ptr(noise), _lib.C.c_float(float(guidance_scale)), ptr(gs), ptr(self.alphas), ptr(t),
+                                _lib.C.c_float(float(view_weight)), ptr(grad), lat.numel(), 1 if accumulate else 0, stream()), 'sds_grad_dev')
         return grad
 
     def _unet(self, x_in, t_in, ctx):
@@ -307,8 +310,8 @@ class Zero123(torch.nn.Module):
         if self.precision == 'bf16':
             with torch.autocast('cuda', dtype=torch.bfloat16):
                 return unet_forward(self.unet, x_in, t_in, ctx).float()
-        if not self.graph:
-            return unet_forward(self.unet, x_in, t_in, ctx)
+        if not self.graph or self._in_chain or torch.cuda.is_current_stream_capturing():
+            return unet_forward(self.unet, x_in, t_in, ctx)      # (inside the whole-chain graph the UNet is captured with the rest)
         if self._graph is None:            # capture once: static inputs, replay afterwards
             self._gx, self._gt, self._gc = x_in.clone(), t_in.clone(), ctx.clone()
             s = torch.cuda.Stream()
@@ -323,41 +326,30 @@ class Zero123(torch.nn.Module):
         self._graph.replay()
         return self._gout
 
-    # -- zero123_utils.py:138-236 ---------------------------------------------------------------------------------------
-    def train_step(self, embeddings, pred_rgb, polar, azimuth, radius, guidance_scale=3, as_latent=False, grad_scale=1,
-                   save_guidance_path=None, t=None, last_grad_scale=None, noise=None, vae_noise=None):
-        dev = pred_rgb.device
+    # -- host prologue of train_step: camera-angle weighting (zero123_utils.py:147-152, :164-175) on CPU tensors -----------------------
+    def _view_weights(self, embeddings, polar, azimuth, radius, grad_scale):
+        """-> (grad_scale [1] CPU tensor, [(view index, weight, T [1,1,4] CPU)] for the reference views with a non-zero weight).
+        Everything here is a function of host-side camera angles: computed on the CPU, so the step never waits for the device."""
         ref_radii, ref_polars, ref_azimuths = embeddings['ref_radii'], embeddings['ref_polars'], embeddings['ref_azimuths']
         polar, azimuth, radius = (torch.as_tensor(v, dtype=torch.float32).reshape(-1).cpu() for v in (polar, azimuth, radius))
         v1 = torch.stack([radius + ref_radii[0], torch.deg2rad(polar + ref_polars[0]), torch.deg2rad(azimuth + ref_azimuths[0])], dim=-1)
         v2 = torch.stack([torch.tensor(ref_radii, dtype=torch.float32), torch.deg2rad(torch.tensor(ref_polars, dtype=torch.float32)),
                           torch.deg2rad(torch.tensor(ref_azimuths, dtype=torch.float32))], dim=-1)
-        angles = torch.rad2deg(self.angle_between(v1, v2)).to(dev)
+        angles = torch.rad2deg(self.angle_between(v1, v2))
         grad_scale = (torch.exp(angles.min(dim=1)[0] / (180 / len(ref_azimuths))) - 1) * grad_scale
-        if as_latent:
-            latents = F.interpolate(pred_rgb, (32, 32), mode='bilinear', align_corners=False) * 2 - 1
-        else:
-            latents = self.encode_imgs(F.interpolate(pred_rgb, (256, 256), mode='bilinear', align_corners=False), noise=vae_noise)
-        if t is None:
-            t = torch.randint(self.min_step, self.max_step + 1, (latents.shape[0],), dtype=torch.long, device=dev)
         if len(ref_azimuths) > 1:
             inv = 1 / angles
             inv[inv > 100] = 100
             inv /= inv.max(dim=-1, keepdim=True)[0]
             inv[inv < 0.1] = 0
         else:
-            inv = torch.tensor([1.0], device=dev)
-        ws = torch.tensor(embeddings['zero123_ws'], dtype=torch.float32, device=dev)[None, :] * inv
+            inv = torch.tensor([1.0])
+        ws = torch.tensor(embeddings['zero123_ws'], dtype=torch.float32)[None, :] * inv
         ws /= ws.max(dim=-1, keepdim=True)[0]
         ws[ws < 0.1] = 0
-        if noise is None:
-            noise = torch.randn_like(latents)
-        w = 1 - self.alphas[t]
-        gsw = (grad_scale * w).reshape(-1)
-        total = torch.zeros_like(latents)
-        # sum_i ws_i * eps_hat_i / sum ws  -  eps   ==  sum_i (ws_i / sum ws) * (eps_hat_i - eps): apply the grad kernel per view
         wsum = ws.sum(dim=-1)
-        for i, (c_crossattn, c_concat) in enumerate(zip(embeddings['c_crossattn'], embeddings['c_concat'])):
+        views = []
+        for i in range(len(ref_azimuths)):
             wi = float(ws[0, i] / wsum[0])
             if wi == 0.0:
                 continue
@@ -365,9 +357,115 @@ class Zero123(torch.nn.Module):
             a = azimuth + ref_azimuths[0] - ref_azimuths[i]
             a = torch.where(a > 180, a - 360, a)
             r = radius + ref_radii[0] - ref_radii[i]
-            T = torch.stack([torch.deg2rad(p), torch.sin(torch.deg2rad(a)), torch.cos(torch.deg2rad(a)), r], dim=-1)[:, None, :].to(dev)
-            total += wi * self.sds_grad(latents, noise, t, c_crossattn.to(dev).reshape(1, 1, -1), c_concat.to(dev), T, guidance_scale, gsw[0])
+            T = torch.stack([torch.deg2rad(p), torch.sin(torch.deg2rad(a)), torch.cos(torch.deg2rad(a)), r], dim=-1)[:, None, :]
+            views.append((i, wi, T))
+        return grad_scale.reshape(-1)[:1].float(), views
+
+    # -- zero123_utils.py:138-236 ---------------------------------------------------------------------------------------
+    def train_step(self, embeddings, pred_rgb, polar, azimuth, radius, guidance_scale=3, as_latent=False, grad_scale=1,
+                   save_guidance_path=None, t=None, last_grad_scale=None, noise=None, vae_noise=None):
+        """-> (loss, t, grad_scale, noise) like the reference.  No device->host synchronisation anywhere in the step; with
+        `graph=True` (and one active reference view, the shipped case: get_virtual_view_loss passes one keyframe, morpheus.py:1044-1088)
+        the WHOLE chain -- bilinear resize, VAE encoder, posterior sample, add-noise, UNet x2 (CFG), SDS gradient, VAE input-gradient
+        backward -- is one CUDA graph replay (`_SDSChainGraph`)."""
+        dev = pred_rgb.device
+        gs_host, views = self._view_weights(embeddings, polar, azimuth, radius, grad_scale)
+        gs_dev = gs_host.to(dev, non_blocking=True)
+        if t is None:
+            t = torch.randint(self.min_step, self.max_step + 1, (pred_rgb.shape[0],), dtype=torch.long, device=dev)
+        t = t.to(dev)
+        if self.graph and not as_latent and len(views) == 1 and pred_rgb.shape[0] == 1 and self.precision != 'bf16':
+            i, wi, T = views[0]
+            shape = (1, 4, 32, 32)
+            if noise is None:
+                noise = torch.randn(shape, device=dev)
+            if vae_noise is None:
+                vae_noise = torch.randn(shape).to(dev, non_blocking=True)       # the reference draws on the CPU (distributions.py:36)
+            loss = _SDSChain.apply(pred_rgb, self, t, noise.to(dev), vae_noise.to(dev), embeddings['c_crossattn'][i].to(dev).reshape(1, 1, -1),
+                                   embeddings['c_concat'][i].to(dev), T.to(dev, non_blocking=True), float(guidance_scale), gs_dev, float(wi))
+            return loss, t, gs_dev, noise
+        if as_latent:
+            latents = F.interpolate(pred_rgb, (32, 32), mode='bilinear', align_corners=False) * 2 - 1
+        else:
+            latents = self.encode_imgs(F.interpolate(pred_rgb, (256, 256), mode='bilinear', align_corners=False), noise=vae_noise)
+        if noise is None:
+            noise = torch.randn_like(latents)
+        total = torch.zeros_like(latents)
+        # sum_i ws_i * eps_hat_i / sum ws  -  eps   ==  sum_i (ws_i / sum ws) * (eps_hat_i - eps): one accumulate launch per view
+        for n_done, (i, wi, T) in enumerate(views):
+            self.sds_grad(latents, noise, t, embeddings['c_crossattn'][i].to(dev).reshape(1, 1, -1), embeddings['c_concat'][i].to(dev),
+                          T.to(dev, non_blocking=True), guidance_scale, gs_dev, view_weight=wi, out=total, accumulate=n_done > 0)
         grad = torch.nan_to_num(total)
         targets = (latents - grad).detach()
         loss = 0.5 * F.mse_loss(latents.float(), targets, reduction='sum') / latents.shape[0]     # d loss / d latents == grad
-        return loss, t, grad_scale, noise
+        return loss, t, gs_dev, noise
+
+    # -- whole-chain CUDA graph ---------------------------------------------------------------------------------------------------
+    def _chain_graph(self, H, W):
+        """capture (once per render resolution) pred_rgb [1,3,H,W] -> (loss, d loss / d pred_rgb) with every per-step quantity in static
+        device buffers.  The VAE runs with autograd enabled INSIDE the capture and torch.autograd.grad produces its input gradient
+        (weights are frozen: dgrad only), so the replay contains forward and backward."""
+        key = (H, W)
+        if key in self._chain:
+            return self._chain[key]
+        dev = self.alphas.device
+        st = {'pred': torch.zeros(1, 3, H, W, device=dev), 't': torch.full((1,), 100, dtype=torch.long, device=dev),
+              'noise': torch.zeros(1, 4, 32, 32, device=dev), 'vae_noise': torch.zeros(1, 4, 32, 32, device=dev),
+              'c_crossattn': torch.zeros(1, 1, 768, device=dev), 'c_concat': torch.zeros(1, 4, 32, 32, device=dev),
+              'T': torch.zeros(1, 1, 4, device=dev), 'gs': torch.ones(1, device=dev)}
+
+        def chain(guidance_scale, wi):
+            self._in_chain = True
+            try:
+                return chain_body(guidance_scale, wi)
+            finally:
+                self._in_chain = False
+
+        def chain_body(guidance_scale, wi):
+            pred = st['pred'].detach().requires_grad_(True)
+            with torch.enable_grad():
+                latents = self.encode_imgs(F.interpolate(pred, (256, 256), mode='bilinear', align_corners=False), noise=st['vae_noise'])
+            total = self.sds_grad(latents, st['noise'], st['t'], st['c_crossattn'], st['c_concat'], st['T'], guidance_scale, st['gs'], view_weight=wi)
+            grad = torch.nan_to_num(total)
+            with _precision(self.precision):
+                g_pred, = torch.autograd.grad(latents, pred, grad)
+            loss = 0.5 * grad.square().sum() / latents.shape[0]       # == 0.5 * mse(latents, (latents - grad).detach(), 'sum') / B
+            return loss, g_pred
+        entry = {'static': st, 'chain': chain, 'graph': None, 'params': None}
+        self._chain[key] = entry
+        return entry
+
+    def _run_chain(self, pred_rgb, t, noise, vae_noise, c_crossattn, c_concat, T, guidance_scale, gs_dev, wi):
+        H, W = int(pred_rgb.shape[2]), int(pred_rgb.shape[3])
+        e = self._chain_graph(H, W)
+        st = e['static']
+        st['pred'].copy_(pred_rgb.detach()); st['t'].copy_(t.reshape(-1)[:1]); st['noise'].copy_(noise); st['vae_noise'].copy_(vae_noise)
+        st['c_crossattn'].copy_(c_crossattn); st['c_concat'].copy_(c_concat); st['T'].copy_(T); st['gs'].copy_(gs_dev.reshape(-1)[:1])
+        if e['graph'] is None or e['params'] != (guidance_scale, wi):      # host scalars are baked into the graph: re-capture when they change
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    e['chain'](guidance_scale, wi)
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                e['out'] = e['chain'](guidance_scale, wi)
+            e['graph'], e['params'] = g, (guidance_scale, wi)
+        e['graph'].replay()
+        return e['out']
+
+
+class _SDSChain(torch.autograd.Function):
+    """pred_rgb -> SDS loss through the whole-chain CUDA graph; backward = upstream * (d loss / d pred_rgb from the replay)"""
+
+    @staticmethod
+    def forward(ctx, pred_rgb, z123, t, noise, vae_noise, c_crossattn, c_concat, T, guidance_scale, gs_dev, wi):
+        loss, g_pred = z123._run_chain(pred_rgb, t, noise, vae_noise, c_crossattn, c_concat, T, guidance_scale, gs_dev, wi)
+        ctx.save_for_backward(g_pred.clone())
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        g_pred, = ctx.saved_tensors
+        return (g_pred * g,) + (None,) * 10

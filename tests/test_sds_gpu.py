@@ -42,12 +42,21 @@ def test_train_step_vs_oracle(graph):
     noise = torch.randn(1, 4, 32, 32, generator=g)
     vae_noise = torch.randn(1, 4, 32, 32, generator=g)
     # ---- ours, twice when graphed (capture, then replay) ----
-    for rep in range(2 if graph else 1):
+    emb_dev = dict(emb, c_crossattn=[c.to(dev) for c in emb['c_crossattn']], c_concat=[c.to(dev) for c in emb['c_concat']])
+    t_dev, noise_dev, vae_noise_dev = t.to(dev), noise.to(dev), vae_noise.to(dev)
+    for rep in range(3 if graph else 2):
         pg = pred.clone().to(dev).requires_grad_(True)
-        loss, t_out, gs, noise_out = z123.train_step(emb, pg, polar, azimuth, radius, guidance_scale=5, grad_scale=0.01, t=t.to(dev),
-                                                     noise=noise.to(dev), vae_noise=vae_noise.to(dev))
-        with guidance._precision('fp32'):      # the VAE backward convolutions must not drop to TF32 either
-            loss.backward()
+        torch.cuda.synchronize()
+        # from the second call on (graphs captured, cuDNN plans cached) the step must not synchronise with the device at all:
+        # abar_t, w(t) and the angle weights never come back to the host (zero123_utils.py:161-212 reads them with .item()-style ops)
+        torch.cuda.set_sync_debug_mode('error' if rep > 0 else 'default')
+        try:
+            loss, t_out, gs, noise_out = z123.train_step(emb_dev, pg, polar, azimuth, radius, guidance_scale=5, grad_scale=0.01, t=t_dev,
+                                                         noise=noise_dev, vae_noise=vae_noise_dev)
+            with guidance._precision('fp32'):      # the VAE backward convolutions must not drop to TF32 either
+                loss.backward()
+        finally:
+            torch.cuda.set_sync_debug_mode('default')
     # ---- oracle chain on the CPU (same functional nets are validated against the reference classes in test_sds_cpu.py) ----
     unet = guidance._KeyIndex({k[len('model.diffusion_model.'):]: v for k, v in sd.items() if k.startswith('model.diffusion_model.')})
     vae = guidance._KeyIndex({k[len('first_stage_model.'):]: v for k, v in sd.items() if k.startswith('first_stage_model.')})
