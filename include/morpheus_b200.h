@@ -215,6 +215,8 @@ int mb_field_backward_warp_tc(const mb_field_params* p, const float* x, const fl
 int mb_occ_update(float* occs, const int64_t* cell_idx, const float* sigma, uint32_t n, float decay, float step,
                   mb_stream_t stream);
 int mb_occ_binarize(const float* occs, uint32_t n, float thre, uint8_t* binaries, mb_stream_t stream);
+/* same with the threshold read from device memory (thre_dev[0]): the refresh then never synchronises with the host */
+int mb_occ_binarize_dev(const float* occs, uint32_t n, const float* thre_dev, uint8_t* binaries, mb_stream_t stream);
 
 /* ---- (6) fused Adam over a flat arena ------------------------------------------------------------ */
 /* p,g,m,v [n]; lr_scale [n_groups] device floats indexed by group_id [n] u8 (per-parameter-group lr,

@@ -104,8 +104,10 @@ __global__ void occ_update_kernel(float* __restrict__ occs, const int64_t* __res
     const int64_t c = idx ? idx[i] : (int64_t)i;
     occs[c] = fmaxf(occs[c] * decay, sigma[i] * step);
 }
-__global__ void occ_binarize_kernel(const float* __restrict__ occs, uint32_t n, float thre, uint8_t* __restrict__ bin) {
+__global__ void occ_binarize_kernel(const float* __restrict__ occs, uint32_t n, float thre, const float* __restrict__ thre_dev,
+                                    uint8_t* __restrict__ bin) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (thre_dev) thre = __ldg(thre_dev);      // device-resident threshold: no device->host round trip in the refresh
     if (i < n) bin[i] = occs[i] > thre ? 1 : 0;
 }
 
@@ -257,8 +259,15 @@ extern "C" int mb_occ_update(float* occs, const int64_t* cell_idx, const float* 
 extern "C" int mb_occ_binarize(const float* occs, uint32_t n, float thre, uint8_t* binaries, mb_stream_t stream) {
     if (n == 0) return MB_OK;
     if (!occs || !binaries) { set_error("occ_binarize: null pointer"); return MB_EINVAL; }
-    occ_binarize_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(occs, n, thre, binaries);
+    occ_binarize_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(occs, n, thre, nullptr, binaries);
     return check_launch("occ_binarize");
+}
+
+extern "C" int mb_occ_binarize_dev(const float* occs, uint32_t n, const float* thre_dev, uint8_t* binaries, mb_stream_t stream) {
+    if (n == 0) return MB_OK;
+    if (!occs || !binaries || !thre_dev) { set_error("occ_binarize_dev: null pointer"); return MB_EINVAL; }
+    occ_binarize_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(occs, n, 0.f, thre_dev, binaries);
+    return check_launch("occ_binarize_dev");
 }
 
 extern "C" int mb_adam_step(float* p, const float* g, float* m, float* v, const uint8_t* group_id, const float* group_lr, uint64_t n,

@@ -150,9 +150,15 @@ class OccGridEstimator(nn.Module):
             self._update(step, occ_eval_fn, occ_thre, ema_decay, warmup_steps)
 
     @torch.no_grad()
-    def _update(self, step, occ_eval_fn, occ_thre, ema_decay, warmup_steps):
+    def _update(self, step, occ_eval_fn, occ_thre, ema_decay, warmup_steps, cell_idx=None, cell_jitter=None):
+        """nerfacc 0.5.x OccGridEstimator._update: cells = all (step < warmup_steps) or N/4 uniform + <= N/4 occupied; x = (ijk + rand) /
+        resolution mapped into the AABB; occs[c] = max(ema_decay * occs[c], occ(x)); binaries = occs > min(mean(occs[occs >= 0]), occ_thre).
+        `cell_idx` / `cell_jitter` inject the two random draws (parity tests).  During warm-up (every cell, the 2 097 152-point refresh)
+        nothing here synchronises with the host: the threshold stays on the device."""
         dev = self.occs.device
-        if step < warmup_steps:
+        if cell_idx is not None:
+            idx = cell_idx.to(dev).long()
+        elif step < warmup_steps:
             idx = self.grid_indices
         else:
             n = self.cells_per_lvl // 4
@@ -162,14 +168,17 @@ class OccGridEstimator(nn.Module):
                 occ_idx = occ_idx[torch.randint(occ_idx.shape[0], (n,), device=dev)]
             idx = torch.cat([uni, occ_idx])
         coords = self.grid_coords[idx]
-        x = (coords + torch.rand_like(coords, dtype=torch.float32)) / self.resolution
+        if cell_jitter is None:
+            cell_jitter = torch.rand_like(coords, dtype=torch.float32)
+        x = (coords + cell_jitter.to(dev)) / self.resolution
         lo, hi = self.aabbs[0, :3], self.aabbs[0, 3:]
         x = lo + x * (hi - lo)
         occ = occ_eval_fn(x).reshape(-1).contiguous().float()   # the reference passes sigma * step_size (morpheus.py:911)
         idx = idx.contiguous()
         check(_lib.lib().mb_occ_update(ptr(self.occs), ptr(idx), ptr(occ), idx.shape[0], C.c_float(ema_decay), C.c_float(1.0), stream()),
               'occ_update')
-        thre = torch.clamp(self.occs[self.occs >= 0].mean(), max=occ_thre)
+        valid = self.occs >= 0
+        thre = torch.clamp((self.occs * valid).sum() / valid.sum().clamp(min=1), max=occ_thre).reshape(1).float().contiguous()
         bin8 = torch.empty(self.cells_per_lvl, dtype=torch.uint8, device=dev)
-        check(_lib.lib().mb_occ_binarize(ptr(self.occs), self.cells_per_lvl, C.c_float(float(thre)), ptr(bin8), stream()), 'occ_binarize')
+        check(_lib.lib().mb_occ_binarize_dev(ptr(self.occs), self.cells_per_lvl, ptr(thre), ptr(bin8), stream()), 'occ_binarize_dev')
         self.binaries = bin8.view(torch.bool).view(self.binaries.shape)

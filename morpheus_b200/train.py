@@ -352,25 +352,61 @@ def virtual_view_loss_terms(out, model, tr):
     return loss
 
 
+class _AllGatherRows(torch.autograd.Function):
+    """[n, C] shard of every rank -> [world * n, C] on every rank (NCCL all-gather); backward hands each rank the rows it contributed.
+    Used for the novel-view image: the rays of the view are rendered ray-sharded, the 62 KB image is gathered, and the (replicated)
+    SDS chain runs on the full image."""
+
+    @staticmethod
+    def forward(ctx, x, world, rank):
+        x = x.contiguous()
+        out = torch.empty((world,) + tuple(x.shape), device=x.device, dtype=x.dtype)
+        dist.all_gather_into_tensor(out, x)
+        ctx.rank, ctx.n = rank, x.shape[0]
+        return out.reshape((world * x.shape[0],) + tuple(x.shape[1:]))
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[ctx.rank * ctx.n:(ctx.rank + 1) * ctx.n].contiguous(), None, None
+
+
 def virtual_view_step(renderer, guidance, opt, view, embeddings, tr, shading='lambertian', ambient_ratio=0.5, bg_color=None,
                       guidance_scale=5.0, grad_weight=0.01, t=None, noise=None, vae_noise=None, light_d=None, world_size=1):
     """One novel-view (SDS) optimiser step: morpheus.py:1147-1236 with real_view=False + get_virtual_view_loss (:1044-1088,
     single reference view) + the regularisers that are live on virtual views (virtual_view_loss_terms).  `view` comes from
-    rays.virtual_view_rays."""
+    rays.virtual_view_rays.  world_size > 1: every rank renders a contiguous slice of the view's rays, the image is all-gathered and
+    the replicated SDS chain runs on the full image (its gradient reaches each rank's slice unscaled; the regularisers are per-shard
+    means and are divided by world_size), then one all-reduce of the flat gradient buffer."""
     model = renderer.model
     opt.set_active(real_view=False, shading=shading)
     opt.zero_grad()
     H, W = view['H'], view['W']
-    out = renderer.render_rays(view['rays_o'], view['rays_d'], view['rays_t'], view['rays_id'], H, W, bg_color=bg_color,
+    rays = {k: view[k].reshape(H * W, -1) for k in ('rays_o', 'rays_d', 'rays_t', 'rays_id')}
+    rank = 0
+    if world_size > 1:
+        rank = dist.get_rank()
+        n = (H * W) // world_size
+        if n * world_size != H * W:
+            raise RuntimeError(f'virtual_view_step: {H}x{W} rays do not split evenly over {world_size} ranks')
+        rays = {k: v[rank * n:(rank + 1) * n] for k, v in rays.items()}
+        if t is None:       # the replicated SDS chain must draw the SAME timestep / noise on every rank
+            g = torch.Generator(device=rays['rays_o'].device).manual_seed(int(opt.t) + 12345)
+            t = torch.randint(guidance.min_step, guidance.max_step + 1, (1,), dtype=torch.long, device=rays['rays_o'].device, generator=g)
+            noise = torch.randn(1, 4, 32, 32, device=rays['rays_o'].device, generator=g) if noise is None else noise
+            vae_noise = torch.randn(1, 4, 32, 32, device=rays['rays_o'].device, generator=g) if vae_noise is None else vae_noise
+    out = renderer.render_rays(rays['rays_o'], rays['rays_d'], rays['rays_t'], rays['rays_id'], H, W, bg_color=bg_color,
                                ambient_ratio=ambient_ratio, light_d=light_d, shading=shading, real_view=False, optimize_pose=False)
-    pred_rgb = out['image'].reshape(1, H, W, 3).permute(0, 3, 1, 2).contiguous()
-    loss, t, grad_scale, noise = guidance.train_step(embeddings, pred_rgb, view['polar'], view['azimuth'], view['radius'],
-                                                     guidance_scale=guidance_scale, grad_scale=grad_weight, t=t, noise=noise, vae_noise=vae_noise)
-    loss = loss + virtual_view_loss_terms(out, model, tr)
-    (loss / world_size).backward()
+    image = out['image'].reshape(-1, 3)
+    if world_size > 1:
+        image = _AllGatherRows.apply(image, world_size, rank)
+    pred_rgb = image.reshape(1, H, W, 3).permute(0, 3, 1, 2).contiguous()
+    loss_sds, t, grad_scale, noise = guidance.train_step(embeddings, pred_rgb, view['polar'], view['azimuth'], view['radius'],
+                                                         guidance_scale=guidance_scale, grad_scale=grad_weight, t=t, noise=noise, vae_noise=vae_noise)
+    reg = virtual_view_loss_terms(out, model, tr)
+    (loss_sds + reg / world_size).backward()
     opt.all_reduce()
     opt.step()
-    return loss.detach(), out
+    return (loss_sds + reg).detach(), out
 
 
 class GraphedStep:

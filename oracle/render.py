@@ -210,3 +210,24 @@ def normal_smoothness_loss(scene, rays_o, rays_d, rays_t, depth, trunc_noise, ph
     w = ortho_normal_dir(n1, phi[keep] if phi.shape[0] == keep.shape[0] else phi)
     n2, _ = scene.normal(pts[keep] + w * smoothness_std, t=ts[keep])
     return torch.mean(torch.square(n1 - n2))
+
+
+# ------------------------------------------------------------------------------------------------
+# occupancy refresh  (nerfacc OccGridEstimator.update_every_n_steps -> _update; call site morpheus.py:905-913)
+# ------------------------------------------------------------------------------------------------
+def occ_grid_update(occs, cell_idx, jitter, aabb, resolution, occ_eval_fn, ema_decay=0.95, occ_thre=0.01):
+    """Published nerfacc 0.5.x semantics (source absent: parity unpinned against nerfacc itself, see the module docstring): the cells
+    `cell_idx` (all of them while step < 256, else N/4 uniform + <= N/4 occupied) are probed at one jittered point each,
+    x = aabb_lo + (ijk + jitter) / resolution * extent with ijk the x-major coordinates of the cell (idx = (ix * res + iy) * res + iz),
+    occs[c] = max(ema_decay * occs[c], occ(x)), binaries = occs > min(mean(occs[occs >= 0]), occ_thre).  -> (occs, binaries)"""
+    ix = cell_idx // (resolution * resolution)
+    iy = (cell_idx // resolution) % resolution
+    iz = cell_idx % resolution
+    coords = torch.stack([ix, iy, iz], dim=-1).to(jitter.dtype)
+    x = (coords + jitter) / resolution
+    x = aabb[:3] + x * (aabb[3:] - aabb[:3])
+    occ = occ_eval_fn(x).reshape(-1)
+    occs = occs.clone()
+    occs[cell_idx] = torch.maximum(occs[cell_idx] * ema_decay, occ)
+    thre = torch.clamp(occs[occs >= 0].mean(), max=occ_thre)
+    return occs, occs > thre

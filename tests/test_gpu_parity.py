@@ -889,3 +889,77 @@ def test_fd_regulariser_vs_fp64_oracle_and_general_path(dev, M, max_level):
     # bar: within 1e-3 of the exact (fp64) gradient, or at least as close to it as the general fp32 path
     bad = {k: e for k, e in errs_o.items() if e > max(1e-3, 1.5 * floor.get(k, 0.0))}
     assert len(errs_o) >= 7 and not bad, f'vs fp64 oracle: {bad}\nfused-vs-oracle {errs_o}\ngeneral-vs-oracle {floor}\nfused-vs-general {errs_g}'
+
+
+# ------------------------------------------------------------------------------------------------
+# occupancy refresh (morpheus.py:905-913 -> nerfacc update_every_n_steps)
+# ------------------------------------------------------------------------------------------------
+def test_occupancy_refresh_vs_oracle(dev):
+    """`Renderer.update_occ_grid` (the fused no-grad density query over the probed cells + mb_occ_update / mb_occ_binarize_dev) against the
+    oracle restatement with the cell jitter and the post-warm-up cell subset injected: the warm-up refresh (every cell) and a later
+    refresh (uniform + occupied subset, EMA decay of the previous values) on a 32^3 grid, then the shipped 128^3 grid against itself
+    (second refresh with the same jitter must reproduce occs / binaries exactly: max(0.95 occs, occ) with occ unchanged)."""
+    from morpheus_b200.nerfacc_compat import OccGridEstimator
+    from morpheus_b200.render import Renderer
+    from oracle import render as orr
+    from oracle.fields import SceneOracle, init_reference_like_state
+    sd = init_reference_like_state(200, seed=13, randomize=True, emb_scale=0.02, sphere=True)
+    sd['sdf2density.beta'] = torch.tensor(0.05)
+    aabb = torch.tensor([-1.01, -1.01, -1.01, 1.01, 1.01, 1.01])
+    res = 32
+    m = make_model(sd, 0.8, dev).train()
+    cfg = {'render': {'step_size': 0.01}, 'model': CONFIG['model'], 'train': {}}
+    est = OccGridEstimator(aabb, res).to(dev).train()
+    R = Renderer(m, est, cfg, 200)
+    rays_t = torch.full((7, 1), 41.0 / 200)
+    sc = SceneOracle(sd, 1.01, 200, 0.8)
+
+    def occ_fn_oracle(x):
+        with torch.no_grad():
+            return sc.density(x, rays_t, allow_shape=True, return_color=False)['sigma'] * 0.01
+
+    def occ_fn_ours(x):
+        return m.density(x, rays_t.to(dev), allow_shape=True, return_color=False)['sigma'] * 0.01
+    g = torch.Generator().manual_seed(5)
+    n = res ** 3
+    # ---- warm-up refresh: every cell ----
+    jit = torch.rand(n, 3, generator=g)
+    est._update(0, occ_fn_ours, 1e-2, 0.95, 256, cell_jitter=jit)
+    occs_o, bin_o = orr.occ_grid_update(torch.zeros(n), torch.arange(n), jit, aabb, res, occ_fn_oracle)
+    assert rel_l2(cpu(est.occs), cpu(occs_o)) < 1e-4
+    mism = (est.binaries.flatten().cpu() != bin_o)
+    near = (occs_o - torch.clamp(occs_o[occs_o >= 0].mean(), max=1e-2)).abs() < 1e-4 * occs_o.abs().clamp(min=1e-6)      # cells sitting ON the threshold
+    assert int((mism & ~near).sum()) == 0 and 0 < int(bin_o.sum()) < n
+    # ---- later refresh: uniform + occupied subset, EMA over the previous state ----
+    uni = torch.randint(n, (n // 4,), generator=g)
+    occ_idx = torch.nonzero(bin_o)[:, 0]
+    if occ_idx.shape[0] > n // 4:
+        occ_idx = occ_idx[torch.randint(occ_idx.shape[0], (n // 4,), generator=g)]
+    idx = torch.cat([uni, occ_idx])
+    jit2 = torch.rand(idx.shape[0], 3, generator=g)
+    # (duplicate cells in idx race in both implementations: keep the first occurrence only)
+    first = torch.zeros(n, dtype=torch.bool)
+    keep = []
+    for k, c in enumerate(idx.tolist()):
+        if not first[c]:
+            first[c] = True
+            keep.append(k)
+    idx, jit2 = idx[keep], jit2[keep]
+    est._update(400, occ_fn_ours, 1e-2, 0.95, 256, cell_idx=idx, cell_jitter=jit2)
+    occs_o2, bin_o2 = orr.occ_grid_update(occs_o, idx, jit2, aabb, res, occ_fn_oracle)
+    assert rel_l2(cpu(est.occs), cpu(occs_o2)) < 1e-4
+    mism = (est.binaries.flatten().cpu() != bin_o2)
+    near = (occs_o2 - torch.clamp(occs_o2[occs_o2 >= 0].mean(), max=1e-2)).abs() < 1e-4 * occs_o2.abs().clamp(min=1e-6)
+    assert int((mism & ~near).sum()) == 0
+    # ---- the shipped 128^3 grid through the public entry point (2 097 152 points, step 0), idempotence of a repeated refresh ----
+    est128 = OccGridEstimator(aabb, 128).to(dev).train()
+    R128 = Renderer(m, est128, cfg, 200)
+    torch.manual_seed(3)
+    R128.update_occ_grid(rays_t.to(dev), step=0)
+    occs1, bin1 = est128.occs.clone(), est128.binaries.clone()
+    assert 0 < int(bin1.sum()) < 128 ** 3
+    torch.manual_seed(3)
+    R128.update_occ_grid(rays_t.to(dev), step=16)        # same jitter: occ unchanged -> max(0.95 occs, occ) == occs
+    assert torch.equal(est128.occs, occs1) and torch.equal(est128.binaries, bin1)
+    R128.update_occ_grid(rays_t.to(dev), step=17)        # not a multiple of 16: no refresh
+    assert torch.equal(est128.occs, occs1)
