@@ -268,7 +268,13 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # leave without destroy_process_group: tearing the communicator down while CUDA graphs that captured its collectives are still
+        # alive can hang; the barrier makes sure every rank has finished its timed region first
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def timed_steps(step_fn, n_warm, n_steps, flush, world, dev, rank, local_rank, after_step=None):

@@ -328,6 +328,6 @@ def test_two_rank_sharded_gradient_equals_single_gpu(dev):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs (gpurun --gpus 2)')
     out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
-                          '--master-port', '29631', os.path.join(ROOT, 'tests', 'dist_step_worker.py')], capture_output=True, text=True, timeout=900)
+                          '--master-port', '29631', os.path.join(ROOT, 'tests', 'dist_step_worker.py')], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert 'SHARDED_OK' in out.stdout, out.stdout[-3000:]
