@@ -3,10 +3,10 @@
 // (external/encoders/gridencoder/src/gridencoder.h:12-13).  Arithmetic follows the reference
 // kernel operation by operation (gridencoder.cu:83-249) with the FMA contractions nvcc applies to
 // it written out explicitly, so results are bit-identical to the reference kernel on the same GPU
-// (tests/test_grid_gpu.py checks this against oracle/_ref).
+// (tests/test_gpu_parity.py::test_grid_encode_bit_exact_vs_reference_kernel checks this against oracle/_ref).
 //
-// B200 design: this op is HBM-bound (12 B in + 128 B out + 384 B dy_dx per sample; tables are
-// L2-resident).  One CTA = 128 consecutive samples x all levels.  outputs[l, b0:b0+128, :] is a
+// B200 design: compulsory HBM traffic is 12 B in + 128 B out + 384 B dy_dx per sample (tables are L2-resident), but for
+// incoherent points the binding resource is the L2 -> SM sector traffic of the 128 eight-byte gathers per sample (tools/time_grid.py).  One CTA = 128 consecutive samples x all levels.  outputs[l, b0:b0+128, :] is a
 // contiguous 1 KB run per level -> coalesced float2 stores straight from registers; the dy_dx
 // tile [128, L*D*C] is one contiguous global block, staged in shared memory and written back
 // with 16-byte coalesced stores (the reference scatters 24-byte pieces at a 384-byte stride).
@@ -57,23 +57,35 @@ __global__ void __launch_bounds__(GE_THREADS) grid_fwd_kernel(const float* __res
             uint32_t pg[D];
 #pragma unroll
             for (uint32_t d = 0; d < D; d++) pos[d] = locate(x[d], res, align_corners, interp, pg[d], deriv[d]);
+            // the 2^D corner values are fetched ONCE (one 8-byte load per corner for C = 2) and feed both the interpolation and the
+            // corner differences of dy_dx (the reference re-reads them: 2^D + D 2^D loads per level).  Hashed levels (tables far larger
+            // than L1) bypass L1 allocation so that the small dense tables of the coarse levels stay resident there.
+            float cval[1u << D][C];
+            const bool stream_level = hashmap_size > 16384u;
+#pragma unroll
+            for (uint32_t idx = 0; idx < (1u << D); idx++) {
+                uint32_t pl[D];
+#pragma unroll
+                for (uint32_t d = 0; d < D; d++) pl[d] = (idx & (1u << d)) ? min(pg[d] + 1, res - 1) : pg[d];
+                const uint32_t index = grid_index<D>(gridtype, hashmap_size, res, pl) * C;
+                if (C == 2) {
+                    float2 v;
+                    if (stream_level) asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(tab + index));
+                    else v = __ldg(reinterpret_cast<const float2*>(tab + index));
+                    cval[idx][0] = v.x;
+                    cval[idx][1 % C] = v.y;
+                } else {
+#pragma unroll
+                    for (uint32_t c = 0; c < C; c++) cval[idx][c] = __ldg(tab + index + c);
+                }
+            }
 #pragma unroll
             for (uint32_t idx = 0; idx < (1u << D); idx++) {
                 float w = 1.0f;
-                uint32_t pl[D];
 #pragma unroll
-                for (uint32_t d = 0; d < D; d++) {
-                    if ((idx & (1u << d)) == 0) {
-                        w = __fmul_rn(w, __fsub_rn(1.0f, pos[d]));
-                        pl[d] = pg[d];
-                    } else {
-                        w = __fmul_rn(w, pos[d]);
-                        pl[d] = min(pg[d] + 1, res - 1);
-                    }
-                }
-                const uint32_t index = grid_index<D>(gridtype, hashmap_size, res, pl) * C;
+                for (uint32_t d = 0; d < D; d++) w = __fmul_rn(w, (idx & (1u << d)) ? pos[d] : __fsub_rn(1.0f, pos[d]));
 #pragma unroll
-                for (uint32_t c = 0; c < C; c++) res_out[c] = __fmaf_rn(w, __ldg(tab + index + c), res_out[c]);
+                for (uint32_t c = 0; c < C; c++) res_out[c] = __fmaf_rn(w, cval[idx][c], res_out[c]);
             }
             if (dy_dx) {
                 const float scale = (float)(align_corners ? res - 1 : res);
@@ -82,25 +94,20 @@ __global__ void __launch_bounds__(GE_THREADS) grid_fwd_kernel(const float* __res
 #pragma unroll
                     for (uint32_t idx = 0; idx < (1u << (D - 1)); idx++) {
                         float w = scale;
-                        uint32_t pl[D];
+                        uint32_t cl = 0;
 #pragma unroll
                         for (uint32_t nd = 0; nd < D - 1; nd++) {
                             const uint32_t d = (nd >= gd) ? (nd + 1) : nd;
                             if ((idx & (1u << nd)) == 0) {
                                 w = __fmul_rn(w, __fsub_rn(1.0f, pos[d]));
-                                pl[d] = pg[d];
                             } else {
                                 w = __fmul_rn(w, pos[d]);
-                                pl[d] = min(pg[d] + 1, res - 1);
+                                cl |= (1u << d);
                             }
                         }
-                        pl[gd] = pg[gd];
-                        const uint32_t il = grid_index<D>(gridtype, hashmap_size, res, pl) * C;
-                        pl[gd] = min(pg[gd] + 1, res - 1);
-                        const uint32_t ir = grid_index<D>(gridtype, hashmap_size, res, pl) * C;
 #pragma unroll
                         for (uint32_t c = 0; c < C; c++) {
-                            const float diff = __fsub_rn(__ldg(tab + ir + c), __ldg(tab + il + c));
+                            const float diff = __fsub_rn(cval[cl | (1u << gd)][c], cval[cl][c]);
                             res_grad[gd][c] = __fmaf_rn(__fmul_rn(w, diff), deriv[gd], res_grad[gd][c]);
                         }
                     }

@@ -34,9 +34,11 @@ lr = mtrain.DEFAULT_TRAIN_CFG['lr']
 
 
 def draws(i):
-    g = torch.Generator().manual_seed(10_000 + i)
-    b = synthetic_real_view_batch(N, seed=3000 + i, frame=(37 * i) % bench.NUM_FRAMES)
-    return ({k: v.to(dev) for k, v in b.items()}, torch.rand(N, generator=g).to(dev), torch.randn(N * S, 3, generator=g).to(dev))
+    with torch.device('cpu'):
+        g = torch.Generator().manual_seed(10_000 + i)
+        b = synthetic_real_view_batch(N, seed=3000 + i, frame=(37 * i) % bench.NUM_FRAMES)
+        jit, noi = torch.rand(N, generator=g), torch.randn(N * S, 3, generator=g)
+    return {k: v.to(dev) for k, v in b.items()}, jit.to(dev), noi.to(dev)
 
 
 # ---- (a) ours ----
