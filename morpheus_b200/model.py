@@ -5,8 +5,10 @@ Same constructor, attribute, method and state_dict surface as the reference clas
 `get_deform_code`, `background`, `pose_optimisation`, `get_RT`, `get_params_all`, `.max_level`,
 `.sdf2density.get_beta()`, `.pose_array`; keys `encoder.embeddings`, `sdf_net.net.N.weight`,
 `deform_net.net.N.weight_g/_v`, `deform_code.volumes.i`, `sdf2density.beta`, `pose_array.data`),
-but every per-sample query runs in ONE fused CUDA launch (csrc/field_fwd.cu) and its backward in
-one more (csrc/field_bwd.cu) instead of ~300 eager kernels with [M, .] intermediates in HBM.
+but every per-sample query runs in ONE fused CUDA launch (csrc/field_fwd_tc.cu, tcgen05; csrc/field_fwd.cu is the fp32 SIMT
+parity engine) and its backward in one to three more (csrc/field_bwd_sdf_tc.cu, field_bwd_fd_tc.cu, field_bwd_tc.cu) instead of
+~300 eager kernels with [M, .] intermediates in HBM; the real-view FD-normal regulariser is one forward+backward launch
+(csrc/field_fd_reg_tc.cu).
 The sub-modules below only own parameters; their torch `forward`s exist for the tiny side paths
 (background colour, code regulariser) that the reference also runs outside the hot loop.
 """

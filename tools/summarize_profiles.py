@@ -65,6 +65,29 @@ def cmd_traffic(rep):
         print(json.dumps({'kernel': d['Kernel Name'][0][:80], 'dram_bytes': b, 'ms': to_ms(*d['gpu__time_duration.sum'])}))
 
 
+BENCH_NAMES = {'fd_reg_tc_kernel': 'fd_regulariser', 'field_fwd_tc_kernel': 'field_fwd_main', 'field_bwd_sdf_tc_kernel': 'field_bwd_sdf_tc_main',
+               'field_bwd_warp_tc_kernel': 'field_bwd_warp_tc', 'field_bwd_fd_tc_kernel': 'field_bwd_fd_tc_main'}
+
+
+def cmd_traffic_json(rep, dst, M, command):
+    """profiles/rNN_traffic.json for bench.py's roofline.traffic: {csrc_sha, M, command, kernels: {bench kernel name: DRAM bytes per launch}}"""
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    kernels, detail = {}, {}
+    for d in raw_metrics(rep):
+        name = d['Kernel Name'][0]
+        key = next((v for k, v in BENCH_NAMES.items() if k in name), None)
+        if key is None or key in kernels:
+            continue
+        kernels[key] = to_bytes(*d['dram__bytes_read.sum']) + to_bytes(*d['dram__bytes_write.sum'])
+        detail[key] = {'dram_read': to_bytes(*d['dram__bytes_read.sum']), 'dram_write': to_bytes(*d['dram__bytes_write.sum']),
+                       'ncu_ms': to_ms(*d['gpu__time_duration.sum'])}
+    json.dump({'csrc_sha': bench.csrc_sha(), 'M': int(M), 'command': command, 'kernels': kernels, 'detail': detail,
+               'what': 'dram__bytes_read.sum + dram__bytes_write.sum per launch from one ncu --set full capture'}, open(dst, 'w'), indent=1)
+    print('wrote', dst, kernels)
+
+
 def cmd_launches(path, dst, command):
     lines = [l for l in open(path) if not l.startswith('==')]
     rows = []
@@ -80,7 +103,7 @@ def cmd_launches(path, dst, command):
     T = sum(v[1] for v in tot.values())
     n_steps = len(adam)
     per_step = (adam[-1] - adam[-2]) if n_steps >= 2 else len(rows)
-    ours = sum(v[1] for k, v in tot.items() if 'mb::' in k or k.startswith(('tc', 'mb', 'tcs', 'tcb')))
+    ours = sum(v[1] for k, v in tot.items() if 'mb::' in k or k.startswith(('tc', 'mb', 'tcs', 'tcb', 'tcr', 'tcf')))
     out = [f'# ncu launch list: `{path.split("/")[-1]}`', '', f'Command (under gpurun, 1x B200): `{command}`', '',
            f'{len(rows)} launches, {n_steps} optimiser steps captured, {per_step} launches per steady-state step; total device time {T:.1f} ms '
            f'(cold-cache, serialised: compare SHARES); our kernels {100 * ours / T:.1f}% of device time.', '',
@@ -98,5 +121,7 @@ if __name__ == '__main__':
         cmd_kernel(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else '')
     elif mode == 'traffic':
         cmd_traffic(sys.argv[2])
+    elif mode == 'traffic-json':
+        cmd_traffic_json(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else '')
     else:
         cmd_launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else '')
