@@ -48,11 +48,13 @@ def peaks():
 
 
 def csrc_sha():
-    """fingerprint of the kernel sources: profiles/r02_traffic.json records the one its ncu capture was taken at"""
+    """fingerprint of the field-kernel sources (the kernels the roofline block reports on): profiles/r02_traffic.json records the one its
+    ncu capture was taken at"""
     h = hashlib.sha1()
     d = os.path.join(ROOT, 'morpheus_b200', 'csrc')
     for f in sorted(os.listdir(d)):
-        h.update(open(os.path.join(d, f), 'rb').read())
+        if f.startswith(('field_', 'tc_', 'common')):
+            h.update(open(os.path.join(d, f), 'rb').read())
     return h.hexdigest()[:12]
 
 

@@ -44,7 +44,9 @@ def timestep_embedding(t, dim, max_period=10000):
 
 
 def _gn(x, sd, prefix, eps):
-    return F.group_norm(x.float(), 32, sd[prefix + '.weight'], sd[prefix + '.bias'], eps).to(x.dtype)
+    w = sd[prefix + '.weight']
+    xf = x if x.dtype == w.dtype else x.to(w.dtype)          # GroupNorm32 computes in the parameter dtype (fp32; fp64 in the precision study)
+    return F.group_norm(xf, 32, w, sd[prefix + '.bias'], eps).to(x.dtype)
 
 
 def _conv(x, sd, prefix, stride=1, padding=1):
@@ -118,7 +120,7 @@ class _KeyIndex(dict):
 def unet_forward(sd, x, t, ctx, model_channels=320):
     """UNetModel.forward(x [B,8,h,w], timesteps [B], context [B,1,768]) -> [B,4,h,w]; sd keys without the
     'model.diffusion_model.' prefix."""
-    emb = _lin(F.silu(_lin(timestep_embedding(t, model_channels), sd, 'time_embed.0')), sd, 'time_embed.2')
+    emb = _lin(F.silu(_lin(timestep_embedding(t, model_channels).to(sd['time_embed.0.weight'].dtype), sd, 'time_embed.0')), sd, 'time_embed.2')
     hs, h = [], x
     i = 0
     while sd.has_prefix(f'input_blocks.{i}.'):
@@ -191,6 +193,9 @@ def vae_encode_moments(sd, img):
     return _conv(h, sd, 'quant_conv', padding=0)
 
 
+_CUDNN_BENCHMARK = True
+
+
 class _precision:
     """'fp32': true fp32 convolutions / matmuls (cuDNN would otherwise pick TF32 for convs by default, ~2e-3 error on the
     SDS gradient); 'reference': exactly what stock PyTorch gives the reference on Ampere+ GPUs (its `fp16: False` path): TF32
@@ -200,12 +205,16 @@ class _precision:
         self.mode = mode
 
     def __enter__(self):
-        self.prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        self.prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
         torch.backends.cudnn.allow_tf32 = self.mode != 'fp32'
         torch.backends.cuda.matmul.allow_tf32 = self.mode not in ('fp32', 'reference')
+        # cuDNN's heuristics pick FFT convolutions for several fp32 layers here (2 112 tiny complex-GEMM launches per step, 43 % of the
+        # fp32 chain: profiles/r02_sds_launches_summary.md); the autotuner (shapes are fixed, results cached) picks implicit-GEMM / Winograd
+        torch.backends.cudnn.benchmark = _CUDNN_BENCHMARK
+        return self
 
     def __exit__(self, *exc):
-        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self.prev
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = self.prev
         return False
 
 

@@ -95,7 +95,7 @@ def cmd_launches(path, dst, command):
         if row.get('Metric Name') != 'gpu__time_duration.sum':
             continue
         rows.append((row['Kernel Name'], to_ms(row['Metric Value'], row['Metric Unit'])))
-    adam = [i for i, (k, _) in enumerate(rows) if 'adam_kernel' in k]
+    adam = [i for i, (k, _) in enumerate(rows) if 'adam_kernel' in k or 'adam_groups_kernel' in k]
     tot = collections.defaultdict(lambda: [0, 0.0])
     for k, ms in rows:
         tot[k.split('(')[0][-70:]][0] += 1
