@@ -274,7 +274,10 @@ class Renderer:
                                                        alpha_thre=0, stratified=True, cone_angle=0.0, early_stop_eps=0, jitter=jitter)
         ray_indices, t_starts, t_ends = samples
         ray_indices = ray_indices.long()
-        if light_d is None:
+        # the light direction only matters when the colour depends on the normal (morpheus.py:641; model.py:523-529): with 'albedo' and with
+        # 'albedo_normal' at ratio 1 (every real view) the lambertian factor is exactly 1, so the draw and its gather are skipped
+        needs_light = shading not in ('albedo',) and not (shading == 'albedo_normal' and float(ambient_ratio) == 1.0)
+        if light_d is None and needs_light:
             light_d = safe_normalize(rays_o + torch.randn(3, device=rays_o.device))
         t_starts, t_ends = t_starts.contiguous().float(), t_ends.contiguous().float()
         ray_indices = ray_indices.contiguous()
@@ -288,7 +291,7 @@ class Renderer:
             depth = torch.zeros([*prefix], device=rays_o.device)
             weights = opacity = normals = deform = normal_raw = None
         else:
-            light = light_d[ray_indices] if shading != 'albedo' else None
+            light = light_d[ray_indices] if (shading != 'albedo' and light_d is not None) else None
             tr_ = cfg.get('train', {}) if model.training else {}
             # real-view training step: with 'albedo_normal' (ratio 1) the colour does not depend on the normal, so the two FD-normal
             # sets of a sample (at x, and at the perturbed point) only feed loss_normal_perturb: ONE fused forward+backward launch
