@@ -252,6 +252,21 @@ int mb_sds_grad_dev(const float* eps_uncond, const float* eps_cond, const float*
                     const float* alphas_cumprod, const int64_t* t_dev, float view_weight, float* grad, uint32_t n, int accumulate,
                     mb_stream_t stream);
 
+/* ---- (7b) tensor-core convolution for the frozen SDS networks (csrc/conv_tc.cu) --------------------------------------------------
+ * 3x3 (stride 1, pad 1; ntaps = 9) or 1x1 (ntaps = 1) convolution as an implicit GEMM on tcgen05 with the 3-term fp16 split (fp32-grade
+ * accuracy).  Replaces F.conv2d of ResBlock / ResnetBlock / proj_in / proj_out (ldm/modules/diffusionmodules/openaimodel.py:256-276,
+ * model.py:82-140, ldm/modules/attention.py:239-253) in strict-fp32 mode; the VAE input-gradient backward is the same kernel on weights
+ * packed with transposed != 0.
+ *   mb_conv_pack_weights: w fp32 [Cout, Cin, kh, kw] -> out (Cout * Cin * ntaps * 4 bytes), n_tile in {128, 160} must divide the packed
+ *                         operator's rows (Cout, or Cin when transposed), 64 its contracted channels
+ *   mb_nchw_split:        x fp32 [B, C, HW] (NCHW) -> hi, lo fp16 [B, HW, C] (NHWC); act = 1 applies SiLU first
+ *   mb_conv_tc:           out fp32 [B, Cout, H, W] = conv(x) + bias; nsplit > 1 splits K over gridDim.z and ACCUMULATES with
+ *                         red.global.add (caller zero-fills out) */
+int mb_conv_pack_weights(const float* w, int Cout, int Cin, int ntaps, int n_tile, int transposed, void* out, mb_stream_t stream);
+int mb_nchw_split(const float* x, int B, int C, int HW, int act, void* hi, void* lo, mb_stream_t stream);
+int mb_conv_tc(const void* x_hi, const void* x_lo, const void* w_packed, const float* bias, float* out, int B, int H, int W, int Cin, int Cout,
+               int ntaps, int n_tile, int nsplit, mb_stream_t stream);
+
 /* ---- (8) host-glue kernels of the step (each replaces tens to hundreds of eager launches) ------------------------- */
 /* xyz[i] = rays_o[ray_indices[i]] + rays_d[ray_indices[i]] * (t_starts[i]+t_ends[i])/2        morpheus.py:645-646 */
 int mb_ray_points_forward(const float* rays_o, const float* rays_d, const int64_t* ray_indices, const float* t_starts,

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libmorpheus_b200.so')
-SOURCES = ['api.cu', 'grid_encode.cu', 'composite.cu', 'sampler.cu', 'field_fwd.cu', 'field_bwd.cu', 'field_fwd_tc.cu', 'field_bwd_tc.cu', 'field_bwd_sdf_tc.cu', 'field_bwd_fd_tc.cu', 'field_fd_reg_tc.cu', 'glue.cu']
+SOURCES = ['api.cu', 'grid_encode.cu', 'composite.cu', 'sampler.cu', 'field_fwd.cu', 'field_bwd.cu', 'field_fwd_tc.cu', 'field_bwd_tc.cu', 'field_bwd_sdf_tc.cu', 'field_bwd_fd_tc.cu', 'field_fd_reg_tc.cu', 'conv_tc.cu', 'glue.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-Xcompiler', '-fPIC',
          '--expt-relaxed-constexpr', '-Xptxas', '-v'] + os.environ.get('MB_NVCC_EXTRA', '').split()

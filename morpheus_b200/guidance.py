@@ -49,8 +49,112 @@ def _gn(x, sd, prefix, eps):
     return F.group_norm(xf, 32, w, sd[prefix + '.bias'], eps).to(x.dtype)
 
 
-def _conv(x, sd, prefix, stride=1, padding=1):
-    return F.conv2d(x, sd[prefix + '.weight'], sd[prefix + '.bias'], stride=stride, padding=padding)
+# ------------------------------------------------------------------------------------------------
+# own tensor-core convolution (csrc/conv_tc.cu) for the strict-fp32 mode
+# ------------------------------------------------------------------------------------------------
+import os as _os
+
+OWN_CONV = _os.environ.get('MORPHEUS_B200_OWN_CONV', '1') != '0'
+_CUR_MODE = ['fp32']          # set by _precision: the own kernels replace cuDNN only where fp32-grade accuracy is asked for
+_CONV_PLANS = {}
+
+
+class _ConvPlan:
+    """frozen weights of one convolution packed for mb_conv_tc (forward) and, lazily, for its input-gradient operator"""
+
+    def __init__(self, w):
+        self.w = w
+        self.Cout, self.Cin, self.k = int(w.shape[0]), int(w.shape[1]), int(w.shape[2])
+        self.ntaps = self.k * self.k
+        self.fwd = self.bwd = None
+
+    @staticmethod
+    def tile(rows):
+        return 128 if rows % 128 == 0 else (160 if rows % 160 == 0 else 0)
+
+    def packed(self, transposed):
+        cur = self.bwd if transposed else self.fwd
+        if cur is None:
+            rows = self.Cin if transposed else self.Cout
+            nt = self.tile(rows)
+            buf = torch.empty(self.Cout * self.Cin * self.ntaps * 4, dtype=torch.uint8, device=self.w.device)
+            check(_lib.lib().mb_conv_pack_weights(ptr(self.w.contiguous()), self.Cout, self.Cin, self.ntaps, nt, 1 if transposed else 0, ptr(buf), stream()),
+                  'conv_pack_weights')
+            cur = (buf, nt)
+            if transposed:
+                self.bwd = cur
+            else:
+                self.fwd = cur
+        return cur
+
+
+def _conv_plan(w):
+    key = w.data_ptr()
+    p = _CONV_PLANS.get(key)
+    if p is None or p.w is not w:
+        p = _CONV_PLANS[key] = _ConvPlan(w)
+    return p
+
+
+def _own_conv_ok(x, w, stride, padding):
+    if not (OWN_CONV and _CUR_MODE[0] == 'fp32' and x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and stride == 1):
+        return False
+    k = int(w.shape[2])
+    if int(w.shape[3]) != k or (k, padding) not in ((3, 1), (1, 0)):
+        return False
+    Cout, Cin = int(w.shape[0]), int(w.shape[1])
+    return Cin % 64 == 0 and Cout % 64 == 0 and _ConvPlan.tile(Cout) != 0
+
+
+def _run_conv_tc(x, plan, bias, transposed, act):
+    """x fp32 NCHW -> fp32 NCHW through nchw_split + conv_tc"""
+    B, C, H, W = (int(v) for v in x.shape)
+    buf, nt = plan.packed(transposed)
+    Cout = plan.Cin if transposed else plan.Cout
+    hi = torch.empty(B, H, W, C, dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi)
+    L = _lib.lib()
+    check(L.mb_nchw_split(ptr(x.contiguous()), B, C, H * W, int(act), ptr(hi), ptr(lo), stream()), 'nchw_split')
+    ctas = ((B * H * W + 127) // 128) * (Cout // nt)
+    n_stages = plan.ntaps * (C // 64)
+    nsplit = max(1, min(n_stages, 148 // ctas)) if ctas < 100 else 1
+    out = (torch.zeros if nsplit > 1 else torch.empty)(B, Cout, H, W, dtype=torch.float32, device=x.device)
+    check(L.mb_conv_tc(ptr(hi), ptr(lo), ptr(buf), ptr(bias) if bias is not None else None, ptr(out), B, H, W, C, Cout, plan.ntaps, nt, nsplit, stream()),
+          'conv_tc')
+    return out
+
+
+class _ConvTC(torch.autograd.Function):
+    """conv2d (3x3 pad 1 / 1x1, stride 1) with FROZEN weights on the tcgen05 kernel; backward = input gradient only (same kernel, transposed pack)"""
+
+    @staticmethod
+    def forward(ctx, x, plan, bias, act):
+        ctx.plan = plan
+        return _run_conv_tc(x, plan, bias, False, act)
+
+    @staticmethod
+    def backward(ctx, g):
+        plan = ctx.plan
+        if _ConvPlan.tile(plan.Cin) == 0:
+            raise RuntimeError('morpheus_b200 conv_tc: input-gradient operator needs C_in divisible by 128 or 160')
+        return _run_conv_tc(g.contiguous().float(), plan, None, True, 0), None, None, None
+
+
+def _conv(x, sd, prefix, stride=1, padding=1, pre_silu=False):
+    """F.conv2d(silu(x) if pre_silu else x, W, b).  Strict-fp32 mode routes the 3x3 / 1x1 stride-1 layers with 64-aligned channels to the own
+    tensor-core kernel (3-term fp16 split); everything else (first / last layers, stride-2 downsamples, TF32 / fp64 modes) stays on cuDNN."""
+    w, b = sd[prefix + '.weight'], sd[prefix + '.bias']
+    if _own_conv_ok(x, w, stride, padding):
+        needs_grad = torch.is_grad_enabled() and x.requires_grad
+        if needs_grad and _ConvPlan.tile(int(w.shape[1])) == 0:
+            needs_grad = None          # no own input-gradient operator for this shape: fall through to cuDNN
+        if needs_grad is not None:
+            if needs_grad and pre_silu:
+                x, pre_silu = F.silu(x), False          # keep the activation in autograd when a gradient flows through it
+            return _ConvTC.apply(x, _conv_plan(w), b, 1 if pre_silu else 0)
+    if pre_silu:
+        x = F.silu(x)
+    return F.conv2d(x, w, b, stride=stride, padding=padding)
 
 
 def _lin(x, sd, prefix):
@@ -62,9 +166,9 @@ def _lin(x, sd, prefix):
 # ------------------------------------------------------------------------------------------------
 def _res_block(h, emb, sd, p):
     x = h
-    h = _conv(F.silu(_gn(h, sd, p + '.in_layers.0', 1e-5)), sd, p + '.in_layers.2')
+    h = _conv(_gn(h, sd, p + '.in_layers.0', 1e-5), sd, p + '.in_layers.2', pre_silu=True)
     h = h + _lin(F.silu(emb), sd, p + '.emb_layers.1')[:, :, None, None]
-    h = _conv(F.silu(_gn(h, sd, p + '.out_layers.0', 1e-5)), sd, p + '.out_layers.3')
+    h = _conv(_gn(h, sd, p + '.out_layers.0', 1e-5), sd, p + '.out_layers.3', pre_silu=True)
     if p + '.skip_connection.weight' in sd:
         x = _conv(x, sd, p + '.skip_connection', padding=0)
     return x + h
@@ -132,7 +236,7 @@ def unet_forward(sd, x, t, ctx, model_channels=320):
     while sd.has_prefix(f'output_blocks.{i}.'):
         h = _unet_block_fast(torch.cat([h, hs.pop()], dim=1), emb, ctx, sd, f'output_blocks.{i}')
         i += 1
-    return _conv(F.silu(_gn(h, sd, 'out.0', 1e-5)), sd, 'out.2')
+    return _conv(_gn(h, sd, 'out.0', 1e-5), sd, 'out.2', pre_silu=True)
 
 
 def _unet_block_fast(h, emb, ctx, sd, p):
@@ -157,8 +261,8 @@ def _unet_block_fast(h, emb, ctx, sd, p):
 # VAE encoder (model.py:368-459) + quant_conv (autoencoder.py:302,324-328)
 # ------------------------------------------------------------------------------------------------
 def _vae_res(x, sd, p):
-    h = _conv(F.silu(_gn(x, sd, p + '.norm1', 1e-6)), sd, p + '.conv1')
-    h = _conv(F.silu(_gn(h, sd, p + '.norm2', 1e-6)), sd, p + '.conv2')
+    h = _conv(_gn(x, sd, p + '.norm1', 1e-6), sd, p + '.conv1', pre_silu=True)
+    h = _conv(_gn(h, sd, p + '.norm2', 1e-6), sd, p + '.conv2', pre_silu=True)
     if p + '.nin_shortcut.weight' in sd:
         x = _conv(x, sd, p + '.nin_shortcut', padding=0)
     return x + h
@@ -189,7 +293,7 @@ def vae_encode_moments(sd, img):
     h = _vae_res(h, sd, 'encoder.mid.block_1')
     h = _vae_attn(h, sd, 'encoder.mid.attn_1')
     h = _vae_res(h, sd, 'encoder.mid.block_2')
-    h = _conv(F.silu(_gn(h, sd, 'encoder.norm_out', 1e-6)), sd, 'encoder.conv_out')
+    h = _conv(_gn(h, sd, 'encoder.norm_out', 1e-6), sd, 'encoder.conv_out', pre_silu=True)
     return _conv(h, sd, 'quant_conv', padding=0)
 
 
@@ -211,10 +315,13 @@ class _precision:
         # cuDNN's heuristics pick FFT convolutions for several fp32 layers here (2 112 tiny complex-GEMM launches per step, 43 % of the
         # fp32 chain: profiles/r02_sds_launches_summary.md); the autotuner (shapes are fixed, results cached) picks implicit-GEMM / Winograd
         torch.backends.cudnn.benchmark = _CUDNN_BENCHMARK
+        self.prev_mode = _CUR_MODE[0]
+        _CUR_MODE[0] = self.mode
         return self
 
     def __exit__(self, *exc):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = self.prev
+        _CUR_MODE[0] = self.prev_mode
         return False
 
 
