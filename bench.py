@@ -544,7 +544,8 @@ def run_virtual_configs(args, rank, world, dev):
                     'note': 'rays are generated on the device (virtual views) / copied from host batches inside the timed step (real views of cfg5)'},
             'sds_chain': {'ms': sds_ms, 'what': 'Zero123.train_step forward + backward to pred_rgb, one CUDA-graph replay (resize, VAE encoder, add-noise, UNet x2 CFG, '
                           'SDS gradient, VAE input-gradient)', 'algorithmic_gflop': sds_flops / 1e9, 'achieved_tflops': sds_flops / (sds_ms * 1e-3) / 1e12,
-                          'library_kernels': 'cuDNN / cuBLAS / SDPA through torch (frozen third-party networks)'},
+                          'kernels': 'fp32 mode: 3x3 / 1x1 stride-1 convolutions of the UNet and the VAE (forward and input-gradient) on the own tcgen05 kernel (csrc/conv_tc.cu); '
+                                     'linear layers, attention, normalisations, stride-2 / first / last convolutions on cuBLAS / SDPA / cuDNN through torch'},
             'roofline': {'kernel': 'Zero-1-to-3 UNet forward (batch 2, inside the SDS chain graph)', 'bound': 'hbm', 'achieved': unet_bytes / (sds_ms * 1e-3) / 1e9,
                          'peak': hbm_peak, 'unit': 'GB/s', 'frac': unet_bytes / (sds_ms * 1e-3) / 1e9 / hbm_peak, 'traffic': None, 'peak_source': which,
                          'note': f'lower bound: {unet_bytes / 1e9:.2f} GB of UNet weights streamed once per step over the WHOLE chain time (the chain also runs the '

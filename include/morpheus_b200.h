@@ -261,11 +261,13 @@ int mb_sds_grad_dev(const float* eps_uncond, const float* eps_cond, const float*
  *                         operator's rows (Cout, or Cin when transposed), 64 its contracted channels
  *   mb_nchw_split:        x fp32 [B, C, HW] (NCHW) -> hi, lo fp16 [B, HW, C] (NHWC); act = 1 applies SiLU first
  *   mb_conv_tc:           out fp32 [B, Cout, H, W] = conv(x) + bias; nsplit > 1 splits K over gridDim.z and ACCUMULATES with
- *                         red.global.add (caller zero-fills out) */
-int mb_conv_pack_weights(const float* w, int Cout, int Cin, int ntaps, int n_tile, int transposed, void* out, mb_stream_t stream);
-int mb_nchw_split(const float* x, int B, int C, int HW, int act, void* hi, void* lo, mb_stream_t stream);
+ *                         red.global.add (caller zero-fills out)
+ * Scaling (fp16 range): weights are multiplied by the power of two `wscale` at pack time, activations by scale_dev[0] (device scalar,
+ * nullable) in the split; the epilogue multiplies the accumulator by out_mul * out_mul_dev[0] (= 1 / wscale, 1 / activation scale). */
+int mb_conv_pack_weights(const float* w, int Cout, int Cin, int ntaps, int n_tile, int transposed, float wscale, void* out, mb_stream_t stream);
+int mb_nchw_split(const float* x, int B, int C, int HW, int act, const float* scale_dev, void* hi, void* lo, mb_stream_t stream);
 int mb_conv_tc(const void* x_hi, const void* x_lo, const void* w_packed, const float* bias, float* out, int B, int H, int W, int Cin, int Cout,
-               int ntaps, int n_tile, int nsplit, mb_stream_t stream);
+               int ntaps, int n_tile, int nsplit, float out_mul, const float* out_mul_dev, mb_stream_t stream);
 
 /* ---- (8) host-glue kernels of the step (each replaces tens to hundreds of eager launches) ------------------------- */
 /* xyz[i] = rays_o[ray_indices[i]] + rays_d[ray_indices[i]] * (t_starts[i]+t_ends[i])/2        morpheus.py:645-646 */

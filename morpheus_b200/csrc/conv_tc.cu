@@ -51,6 +51,8 @@ struct Args {
     const float* bias;       // [Cout] or NULL
     float* out;              // [B, Cout, H, W] fp32 (NCHW)
     int B, H, W, Cin, Cout, ntaps;      // ntaps = 9 (3x3, pad 1) or 1 (1x1)
+    float out_mul;           // epilogue factor: 1 / (weight scale chosen at pack time)
+    const float* out_mul_dev;   // optional device factor: 1 / (activation scale applied by nchw_split_kernel), or NULL
 };
 
 template <int N_TILE>
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const Args a) {
         tc_fence_after();
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
         float* obase = a.out + (size_t)b * a.Cout * HW + rem;
+        const float omul = a.out_mul * (a.out_mul_dev ? __ldg(a.out_mul_dev) : 1.0f);
 #pragma unroll 1
         for (int cbk = 0; cbk < N_TILE / 32; cbk++) {
             float v[32];
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const Args a) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     const int n = nt * N_TILE + cbk * 32 + j;
-                    float val = v[j];
+                    float val = v[j] * omul;
                     if (a.bias && z == 0) val += __ldg(a.bias + n);
                     float* dst = obase + (size_t)n * HW;
                     if (nsplit > 1) atomicAdd(dst, val);
@@ -186,7 +189,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const Args a) {
 
 // ---- weight packing: fp32 [Cout, Cin, kh, kw] -> per (n-tile, tap, 64-channel block) stage blocks in UMMA canonical K-major order (hi | lo) ----
 // transposed != 0 packs the input-gradient operator: rows = C_in of the forward layer, K = C_out, taps flipped (dx = conv(dy, W^T flipped)).
-__global__ void pack_conv_kernel(const float* __restrict__ w, int Cout_w, int Cin_w, int ntaps, int n_tile, int transposed, uint8_t* __restrict__ out) {
+__global__ void pack_conv_kernel(const float* __restrict__ w, int Cout_w, int Cin_w, int ntaps, int n_tile, int transposed, float wscale,
+                                 uint8_t* __restrict__ out) {
     const int N = transposed ? Cin_w : Cout_w;        // rows of the packed operator
     const int K = transposed ? Cout_w : Cin_w;        // channels contracted per tap
     const int cblocks = K / KC, n_tiles = N / n_tile;
@@ -199,6 +203,7 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int Cout_w, int Ci
         float v;
         if (!transposed) v = w[((size_t)n * Cin_w + c) * ntaps + tap];
         else v = w[((size_t)c * Cin_w + n) * ntaps + (ntaps - 1 - tap)];
+        v *= wscale;      // power of two chosen by the host so that max |w| ~ 2^8: hi AND lo parts stay normal fp16 numbers (full 22 bits)
         const __half h = __float2half_rn(v);
         const __half l = __float2half_rn(v - __half2float(h));
         const int nt = n / n_tile, nn = n - nt * n_tile;
@@ -212,16 +217,20 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int Cout_w, int Ci
 }
 
 // ---- activation split: fp32 NCHW -> fp16 (hi, lo) NHWC planes, optional SiLU (x * sigmoid(x)) applied first ----
-__global__ void nchw_split_kernel(const float* __restrict__ x, int C, int HW, int act, __half* __restrict__ hi, __half* __restrict__ lo) {
+__global__ void nchw_split_kernel(const float* __restrict__ x, int C, int HW, int act, const float* __restrict__ scale_dev, __half* __restrict__ hi,
+                                  __half* __restrict__ lo) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 256 threads: 8 rows per pass
+    // dynamic power-of-two scale (gradients of the VAE backward are ~1e-6: below fp16's normal range without it)
+    const float sc = scale_dev ? __ldg(scale_dev) : 1.0f;
     for (int j = ty; j < 32; j += 8) {
         const int c = c0 + j, p = p0 + tx;
         float v = 0.f;
         if (c < C && p < HW) {
             v = x[((size_t)b * C + c) * HW + p];
             if (act == 1) v = v / (1.0f + expf(-v));
+            v *= sc;
         }
         tile[j][tx] = v;
     }
@@ -256,27 +265,27 @@ int launch(const Args& a, int nsplit, cudaStream_t stream) {
 }  // namespace conv
 }  // namespace mb
 
-extern "C" int mb_conv_pack_weights(const float* w, int Cout, int Cin, int ntaps, int n_tile, int transposed, void* out, mb_stream_t stream) {
+extern "C" int mb_conv_pack_weights(const float* w, int Cout, int Cin, int ntaps, int n_tile, int transposed, float wscale, void* out, mb_stream_t stream) {
     using namespace mb;
     const int N = transposed ? Cin : Cout, K = transposed ? Cout : Cin;
     if (!w || !out || (ntaps != 9 && ntaps != 1) || (n_tile != 128 && n_tile != 160) || N % n_tile || K % conv::KC) {
         set_error("conv_pack_weights: need ntaps in {1, 9}, n_tile in {128, 160}, rows %% n_tile == 0, channels %% 64 == 0");
         return MB_EINVAL;
     }
-    conv::pack_conv_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, ntaps, n_tile, transposed, (uint8_t*)out);
+    conv::pack_conv_kernel<<<1024, 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, ntaps, n_tile, transposed, wscale, (uint8_t*)out);
     return check_launch("conv_pack_weights");
 }
 
-extern "C" int mb_nchw_split(const float* x, int B, int C, int HW, int act, void* hi, void* lo, mb_stream_t stream) {
+extern "C" int mb_nchw_split(const float* x, int B, int C, int HW, int act, const float* scale_dev, void* hi, void* lo, mb_stream_t stream) {
     using namespace mb;
     if (!x || !hi || !lo || B <= 0 || C <= 0 || HW <= 0) { set_error("nchw_split: bad argument"); return MB_EINVAL; }
     dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
-    conv::nchw_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, C, HW, act, (__half*)hi, (__half*)lo);
+    conv::nchw_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, C, HW, act, scale_dev, (__half*)hi, (__half*)lo);
     return check_launch("nchw_split");
 }
 
 extern "C" int mb_conv_tc(const void* x_hi, const void* x_lo, const void* w_packed, const float* bias, float* out, int B, int H, int W, int Cin, int Cout,
-                          int ntaps, int n_tile, int nsplit, mb_stream_t stream) {
+                          int ntaps, int n_tile, int nsplit, float out_mul, const float* out_mul_dev, mb_stream_t stream) {
     using namespace mb;
     if (!x_hi || !x_lo || !w_packed || !out) { set_error("conv_tc: null pointer"); return MB_EINVAL; }
     if ((ntaps != 9 && ntaps != 1) || (n_tile != 128 && n_tile != 160) || Cout % n_tile || Cin % conv::KC || B <= 0 || H <= 0 || W <= 0) {
@@ -286,6 +295,6 @@ extern "C" int mb_conv_tc(const void* x_hi, const void* x_lo, const void* w_pack
     const int n_stages = ntaps * (Cin / conv::KC);
     if (nsplit < 1) nsplit = 1;
     if (nsplit > n_stages) nsplit = n_stages;
-    conv::Args a{(const __half*)x_hi, (const __half*)x_lo, (const uint8_t*)w_packed, bias, out, B, H, W, Cin, Cout, ntaps};
+    conv::Args a{(const __half*)x_hi, (const __half*)x_lo, (const uint8_t*)w_packed, bias, out, B, H, W, Cin, Cout, ntaps, out_mul, out_mul_dev};
     return n_tile == 128 ? conv::launch<128>(a, nsplit, (cudaStream_t)stream) : conv::launch<160>(a, nsplit, (cudaStream_t)stream);
 }

@@ -67,6 +67,9 @@ class _ConvPlan:
         self.Cout, self.Cin, self.k = int(w.shape[0]), int(w.shape[1]), int(w.shape[2])
         self.ntaps = self.k * self.k
         self.fwd = self.bwd = None
+        # power-of-two weight scale (init-time, the weights are frozen): max |w| -> [256, 512) keeps the hi AND lo fp16 parts normal
+        amax = float(w.detach().abs().max())
+        self.wscale = float(2.0 ** (8 - math.floor(math.log2(amax)))) if amax > 0 and math.isfinite(amax) else 1.0
 
     @staticmethod
     def tile(rows):
@@ -78,7 +81,8 @@ class _ConvPlan:
             rows = self.Cin if transposed else self.Cout
             nt = self.tile(rows)
             buf = torch.empty(self.Cout * self.Cin * self.ntaps * 4, dtype=torch.uint8, device=self.w.device)
-            check(_lib.lib().mb_conv_pack_weights(ptr(self.w.contiguous()), self.Cout, self.Cin, self.ntaps, nt, 1 if transposed else 0, ptr(buf), stream()),
+            check(_lib.lib().mb_conv_pack_weights(ptr(self.w.contiguous()), self.Cout, self.Cin, self.ntaps, nt, 1 if transposed else 0,
+                                                  _lib.C.c_float(self.wscale), ptr(buf), stream()),
                   'conv_pack_weights')
             cur = (buf, nt)
             if transposed:
@@ -106,21 +110,27 @@ def _own_conv_ok(x, w, stride, padding):
     return Cin % 64 == 0 and Cout % 64 == 0 and _ConvPlan.tile(Cout) != 0
 
 
-def _run_conv_tc(x, plan, bias, transposed, act):
-    """x fp32 NCHW -> fp32 NCHW through nchw_split + conv_tc"""
+def _run_conv_tc(x, plan, bias, transposed, act, dynamic_scale=False):
+    """x fp32 NCHW -> fp32 NCHW through nchw_split + conv_tc.  dynamic_scale: multiply x by a power of two chosen ON THE DEVICE from max |x|
+    (no host sync) before the fp16 split -- the gradients of the VAE backward are ~1e-6, below fp16's normal range."""
     B, C, H, W = (int(v) for v in x.shape)
     buf, nt = plan.packed(transposed)
     Cout = plan.Cin if transposed else plan.Cout
     hi = torch.empty(B, H, W, C, dtype=torch.float16, device=x.device)
     lo = torch.empty_like(hi)
     L = _lib.lib()
-    check(L.mb_nchw_split(ptr(x.contiguous()), B, C, H * W, int(act), ptr(hi), ptr(lo), stream()), 'nchw_split')
+    sc = inv = None
+    if dynamic_scale:
+        amax = x.detach().abs().amax().clamp(min=1e-30)
+        sc = torch.exp2(9.0 - torch.floor(torch.log2(amax))).reshape(1)
+        inv = (1.0 / sc).contiguous()
+    check(L.mb_nchw_split(ptr(x.contiguous()), B, C, H * W, int(act), ptr(sc), ptr(hi), ptr(lo), stream()), 'nchw_split')
     ctas = ((B * H * W + 127) // 128) * (Cout // nt)
     n_stages = plan.ntaps * (C // 64)
     nsplit = max(1, min(n_stages, 148 // ctas)) if ctas < 100 else 1
     out = (torch.zeros if nsplit > 1 else torch.empty)(B, Cout, H, W, dtype=torch.float32, device=x.device)
-    check(L.mb_conv_tc(ptr(hi), ptr(lo), ptr(buf), ptr(bias) if bias is not None else None, ptr(out), B, H, W, C, Cout, plan.ntaps, nt, nsplit, stream()),
-          'conv_tc')
+    check(L.mb_conv_tc(ptr(hi), ptr(lo), ptr(buf), ptr(bias) if bias is not None else None, ptr(out), B, H, W, C, Cout, plan.ntaps, nt, nsplit,
+                       _lib.C.c_float(1.0 / plan.wscale), ptr(inv), stream()), 'conv_tc')
     return out
 
 
@@ -137,7 +147,7 @@ class _ConvTC(torch.autograd.Function):
         plan = ctx.plan
         if _ConvPlan.tile(plan.Cin) == 0:
             raise RuntimeError('morpheus_b200 conv_tc: input-gradient operator needs C_in divisible by 128 or 160')
-        return _run_conv_tc(g.contiguous().float(), plan, None, True, 0), None, None, None
+        return _run_conv_tc(g.contiguous().float(), plan, None, True, 0, dynamic_scale=True), None, None, None
 
 
 def _conv(x, sd, prefix, stride=1, padding=1, pre_silu=False):

@@ -46,7 +46,7 @@ def test_conv_tc_vs_float64(case):
             y_silu = guidance._conv(x, sd, 'c', padding=pad, pre_silu=True)
         xg = x.clone().requires_grad_(True)
         yg = guidance._conv(xg, sd, 'c', padding=pad, pre_silu=True)
-        gout = torch.randn(yg.shape, generator=g).to(dev)
+        gout = torch.randn(yg.shape, generator=g).to(dev) * 1e-6        # VAE-backward-sized gradients: exercises the dynamic power-of-two scale
         yg.backward(gout)
         y_cudnn = F.conv2d(x, w, b, padding=pad)
     xd = x.double().requires_grad_(True)
@@ -54,10 +54,10 @@ def test_conv_tc_vs_float64(case):
     ref_silu = F.conv2d(F.silu(xd), w.double(), b.double(), padding=pad)
     ref_silu.backward(gout.double())
     e = rel(y, ref)
-    assert e < 2e-6, e
+    assert e < 3e-6, e          # (K up to 11 520 with split-K atomics; cuDNN's fp32 result sits at 2.6e-6 on the 320-channel case)
     assert rel(y_silu, ref_silu) < 2e-6
     assert rel(yg, ref_silu) < 2e-6
-    assert rel(xg.grad, xd.grad) < 2e-6, rel(xg.grad, xd.grad)
+    assert rel(xg.grad, xd.grad) < 5e-6, rel(xg.grad, xd.grad)      # (includes the fp32 SiLU backward of torch)
     print(f'conv {case}: own {e:.1e}, cuDNN fp32 {rel(y_cudnn, ref):.1e}')
 
 
