@@ -267,7 +267,10 @@ int mb_sds_grad_dev(const float* eps_uncond, const float* eps_cond, const float*
 int mb_conv_pack_weights(const float* w, int Cout, int Cin, int ntaps, int n_tile, int transposed, float wscale, void* out, mb_stream_t stream);
 int mb_nchw_split(const float* x, int B, int C, int HW, int act, const float* scale_dev, void* hi, void* lo, mb_stream_t stream);
 int mb_conv_tc(const void* x_hi, const void* x_lo, const void* w_packed, const float* bias, float* out, int B, int H, int W, int Cin, int Cout,
-               int ntaps, int n_tile, int nsplit, float out_mul, const float* out_mul_dev, mb_stream_t stream);
+               int ntaps, int n_tile, int nsplit, float out_mul, const float* out_mul_dev, int out_rows, mb_stream_t stream);
+/* linear layers of the UNet's transformer blocks (ldm/modules/attention.py:37-64, :152-193) = 1x1 convolution over tokens: x [rows, C] fp32
+ * (row-major) -> hi, lo fp16 of the same layout; mb_conv_tc with B = 1, H = rows, W = 1, ntaps = 1, out_rows = 1 writes out [rows, Cout] */
+int mb_rows_split(const float* x, uint64_t n_elems, const float* scale_dev, void* hi, void* lo, mb_stream_t stream);
 
 /* ---- (8) host-glue kernels of the step (each replaces tens to hundreds of eager launches) ------------------------- */
 /* xyz[i] = rays_o[ray_indices[i]] + rays_d[ray_indices[i]] * (t_starts[i]+t_ends[i])/2        morpheus.py:645-646 */

@@ -63,7 +63,7 @@ SHADE = {'albedo': 0, 'lambertian': 1, 'albedo_normal': 1, 'textureless': 2, 'no
 SYMBOLS = ['mb_version', 'mb_last_error', 'mb_sm_count', 'mb_grid_encode_forward', 'mb_grid_encode_backward',
            'mb_sample_rays_count', 'mb_sample_rays_write', 'mb_sample_rays_uniform', 'mb_composite_forward',
            'mb_composite_backward', 'mb_field_forward', 'mb_field_backward', 'mb_occ_update', 'mb_occ_binarize', 'mb_occ_binarize_dev',
-           'mb_adam_step', 'mb_sds_grad', 'mb_add_noise', 'mb_sds_grad_dev', 'mb_add_noise_dev', 'mb_conv_pack_weights', 'mb_nchw_split', 'mb_conv_tc', 'mb_pack_tc', 'mb_field_forward_tc', 'mb_adam_step_dev', 'mb_adam_step_groups', 'mb_field_backward_warp_tc', 'mb_field_backward_sdf_tc',
+           'mb_adam_step', 'mb_sds_grad', 'mb_add_noise', 'mb_sds_grad_dev', 'mb_add_noise_dev', 'mb_conv_pack_weights', 'mb_nchw_split', 'mb_conv_tc', 'mb_rows_split', 'mb_pack_tc', 'mb_field_forward_tc', 'mb_adam_step_dev', 'mb_adam_step_groups', 'mb_field_backward_warp_tc', 'mb_field_backward_sdf_tc',
            'mb_ray_points_forward', 'mb_ray_points_backward', 'mb_pack_arena_forward', 'mb_pack_arena_backward', 'mb_sdf_loss_forward',
            'mb_sdf_loss_backward', 'mb_pose_rays_forward', 'mb_pose_rays_backward', 'mb_ray_loss', 'mb_field_backward_fd_tc', 'mb_fd_regulariser_tc', 'mb_debug_fd_phases', 'mb_debug_fdr_phases', 'mb_code_reg']
 

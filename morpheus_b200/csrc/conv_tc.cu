@@ -53,6 +53,7 @@ struct Args {
     int B, H, W, Cin, Cout, ntaps;      // ntaps = 9 (3x3, pad 1) or 1 (1x1)
     float out_mul;           // epilogue factor: 1 / (weight scale chosen at pack time)
     const float* out_mul_dev;   // optional device factor: 1 / (activation scale applied by nchw_split_kernel), or NULL
+    int out_rows;            // != 0: out is row-major [B H W, Cout] (token-major linear layer) instead of NCHW
 };
 
 template <int N_TILE>
@@ -134,14 +135,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const Args a) {
             float v[32];
             tmem_ld32(tmem + lane_base + cbk * 32, v);
             if (pvalid && n_st > 0) {
+                const int n0 = nt * N_TILE + cbk * 32;
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
-                    const int n = nt * N_TILE + cbk * 32 + j;
-                    float val = v[j] * omul;
-                    if (a.bias && z == 0) val += __ldg(a.bias + n);
-                    float* dst = obase + (size_t)n * HW;
-                    if (nsplit > 1) atomicAdd(dst, val);
-                    else *dst = val;
+                    v[j] *= omul;
+                    if (a.bias && z == 0) v[j] += __ldg(a.bias + n0 + j);
+                }
+                if (a.out_rows) {
+                    // token-major output: this thread owns 32 consecutive floats of its row
+                    float* dst = a.out + (size_t)p * a.Cout + n0;
+                    if (nsplit > 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        float* dst = obase + (size_t)(n0 + j) * HW;
+                        if (nsplit > 1) atomicAdd(dst, v[j]);
+                        else *dst = v[j];
+                    }
                 }
             }
         }
@@ -247,6 +263,18 @@ __global__ void nchw_split_kernel(const float* __restrict__ x, int C, int HW, in
     }
 }
 
+// ---- row-major activations [rows, C] fp32 (tokens of a linear layer) -> fp16 (hi, lo) planes of the same layout ----
+__global__ void rows_split_kernel(const float* __restrict__ x, size_t n, const float* __restrict__ scale_dev, __half* __restrict__ hi, __half* __restrict__ lo) {
+    const float sc = scale_dev ? __ldg(scale_dev) : 1.0f;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n; i += (size_t)gridDim.x * blockDim.x * 2) {
+        const float2 v = *reinterpret_cast<const float2*>(x + i);
+        const __half2 h = __floats2half2_rn(v.x * sc, v.y * sc);
+        const float2 hf = __half22float2(h);
+        *reinterpret_cast<__half2*>(hi + i) = h;
+        *reinterpret_cast<__half2*>(lo + i) = __floats2half2_rn(v.x * sc - hf.x, v.y * sc - hf.y);
+    }
+}
+
 template <int N_TILE>
 int launch(const Args& a, int nsplit, cudaStream_t stream) {
     using S = Smem<N_TILE>;
@@ -284,8 +312,17 @@ extern "C" int mb_nchw_split(const float* x, int B, int C, int HW, int act, cons
     return check_launch("nchw_split");
 }
 
+extern "C" int mb_rows_split(const float* x, uint64_t n_elems, const float* scale_dev, void* hi, void* lo, mb_stream_t stream) {
+    using namespace mb;
+    if (!x || !hi || !lo || (n_elems & 1)) { set_error("rows_split: bad argument (even element count)"); return MB_EINVAL; }
+    if (n_elems == 0) return MB_OK;
+    const unsigned blocks = (unsigned)min<uint64_t>((n_elems / 2 + 255) / 256, 148 * 16);
+    conv::rows_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (size_t)n_elems, scale_dev, (__half*)hi, (__half*)lo);
+    return check_launch("rows_split");
+}
+
 extern "C" int mb_conv_tc(const void* x_hi, const void* x_lo, const void* w_packed, const float* bias, float* out, int B, int H, int W, int Cin, int Cout,
-                          int ntaps, int n_tile, int nsplit, float out_mul, const float* out_mul_dev, mb_stream_t stream) {
+                          int ntaps, int n_tile, int nsplit, float out_mul, const float* out_mul_dev, int out_rows, mb_stream_t stream) {
     using namespace mb;
     if (!x_hi || !x_lo || !w_packed || !out) { set_error("conv_tc: null pointer"); return MB_EINVAL; }
     if ((ntaps != 9 && ntaps != 1) || (n_tile != 128 && n_tile != 160) || Cout % n_tile || Cin % conv::KC || B <= 0 || H <= 0 || W <= 0) {
@@ -295,6 +332,6 @@ extern "C" int mb_conv_tc(const void* x_hi, const void* x_lo, const void* w_pack
     const int n_stages = ntaps * (Cin / conv::KC);
     if (nsplit < 1) nsplit = 1;
     if (nsplit > n_stages) nsplit = n_stages;
-    conv::Args a{(const __half*)x_hi, (const __half*)x_lo, (const uint8_t*)w_packed, bias, out, B, H, W, Cin, Cout, ntaps, out_mul, out_mul_dev};
+    conv::Args a{(const __half*)x_hi, (const __half*)x_lo, (const uint8_t*)w_packed, bias, out, B, H, W, Cin, Cout, ntaps, out_mul, out_mul_dev, out_rows};
     return n_tile == 128 ? conv::launch<128>(a, nsplit, (cudaStream_t)stream) : conv::launch<160>(a, nsplit, (cudaStream_t)stream);
 }

@@ -63,7 +63,7 @@ class _ConvPlan:
     """frozen weights of one convolution packed for mb_conv_tc (forward) and, lazily, for its input-gradient operator"""
 
     def __init__(self, w):
-        self.w = w
+        self.w = self.w_src = w
         self.Cout, self.Cin, self.k = int(w.shape[0]), int(w.shape[1]), int(w.shape[2])
         self.ntaps = self.k * self.k
         self.fwd = self.bwd = None
@@ -92,10 +92,20 @@ class _ConvPlan:
         return cur
 
 
+def _linear_plan(w):
+    """a Linear weight [N, K] is the 1x1 convolution weight [N, K, 1, 1]"""
+    key = w.data_ptr()
+    p = _CONV_PLANS.get(key)
+    if p is None or p.w_src is not w:
+        p = _CONV_PLANS[key] = _ConvPlan(w.reshape(w.shape[0], w.shape[1], 1, 1))
+        p.w_src = w
+    return p
+
+
 def _conv_plan(w):
     key = w.data_ptr()
     p = _CONV_PLANS.get(key)
-    if p is None or p.w is not w:
+    if p is None or p.w_src is not w:
         p = _CONV_PLANS[key] = _ConvPlan(w)
     return p
 
@@ -130,8 +140,28 @@ def _run_conv_tc(x, plan, bias, transposed, act, dynamic_scale=False):
     nsplit = max(1, min(n_stages, 148 // ctas)) if ctas < 100 else 1
     out = (torch.zeros if nsplit > 1 else torch.empty)(B, Cout, H, W, dtype=torch.float32, device=x.device)
     check(L.mb_conv_tc(ptr(hi), ptr(lo), ptr(buf), ptr(bias) if bias is not None else None, ptr(out), B, H, W, C, Cout, plan.ntaps, nt, nsplit,
-                       _lib.C.c_float(1.0 / plan.wscale), ptr(inv), stream()), 'conv_tc')
+                       _lib.C.c_float(1.0 / plan.wscale), ptr(inv), 0, stream()), 'conv_tc')
     return out
+
+
+def _run_linear_tc(x, plan, bias):
+    """x [.., C] fp32 -> [.., N]: the linear layer as a 1x1 convolution over its tokens on the own tensor-core kernel (no-grad paths only)"""
+    C = int(x.shape[-1])
+    rows = x.numel() // C
+    buf, nt = plan.packed(False)
+    N = plan.Cout
+    x2 = x.contiguous()
+    hi = torch.empty(rows, C, dtype=torch.float16, device=x.device)
+    lo = torch.empty_like(hi)
+    L = _lib.lib()
+    check(L.mb_rows_split(ptr(x2), _lib.C.c_uint64(rows * C), None, ptr(hi), ptr(lo), stream()), 'rows_split')
+    ctas = ((rows + 127) // 128) * (N // nt)
+    n_stages = C // 64
+    nsplit = max(1, min(n_stages, 148 // ctas)) if ctas < 100 else 1
+    out = (torch.zeros if nsplit > 1 else torch.empty)(rows, N, dtype=torch.float32, device=x.device)
+    check(L.mb_conv_tc(ptr(hi), ptr(lo), ptr(buf), ptr(bias) if bias is not None else None, ptr(out), 1, rows, 1, C, N, 1, nt, nsplit,
+                       _lib.C.c_float(1.0 / plan.wscale), None, 1, stream()), 'conv_tc(linear)')
+    return out.view(*x.shape[:-1], N)
 
 
 class _ConvTC(torch.autograd.Function):
@@ -168,7 +198,12 @@ def _conv(x, sd, prefix, stride=1, padding=1, pre_silu=False):
 
 
 def _lin(x, sd, prefix):
-    return F.linear(x, sd[prefix + '.weight'], sd.get(prefix + '.bias'))
+    w, b = sd[prefix + '.weight'], sd.get(prefix + '.bias')
+    # token-major linear layers of the (no-grad) UNet transformer blocks: own tensor-core kernel in strict-fp32 mode
+    if (OWN_CONV and _CUR_MODE[0] == 'fp32' and x.is_cuda and x.dtype == torch.float32 and w.dtype == torch.float32 and not torch.is_grad_enabled()
+            and x.dim() == 3 and x.numel() // x.shape[-1] >= 128 and w.shape[1] % 64 == 0 and _ConvPlan.tile(int(w.shape[0])) != 0):
+        return _run_linear_tc(x, _linear_plan(w), b)
+    return F.linear(x, w, b)
 
 
 # ------------------------------------------------------------------------------------------------

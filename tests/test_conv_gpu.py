@@ -97,3 +97,25 @@ def test_sds_chain_with_own_convs_matches_cudnn_path():
             guidance.OWN_CONV = True
     assert abs(res[True][0] - res[False][0]) <= 1e-4 * abs(res[False][0])
     assert rel(res[True][1], res[False][1]) < 1e-4, rel(res[True][1], res[False][1])
+
+
+@pytest.mark.parametrize('shape', [(2, 1024, 320, 320), (2, 1024, 320, 2560), (2, 256, 2560, 640), (2, 64, 1280, 1280), (1, 200, 64, 128)])
+def test_linear_tc_vs_float64(shape):
+    """token-major linear layers of the UNet transformer blocks through the same kernel (1x1 convolution over tokens, row-major output)"""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from morpheus_b200 import guidance
+    Bt, T, K, N = shape
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(K + N + T)
+    x = torch.randn(Bt, T, K, generator=g).to(dev)
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    sd = {'l.weight': w, 'l.bias': b, 'n.weight': w}
+    with guidance._precision('fp32'), torch.no_grad():
+        y = guidance._lin(x, sd, 'l')
+        y_nobias = guidance._lin(x, sd, 'n')
+    ref = F.linear(x.double(), w.double(), b.double())
+    assert y.shape == ref.shape
+    assert rel(y, ref) < 2e-6, rel(y, ref)
+    assert rel(y_nobias, F.linear(x.double(), w.double())) < 2e-6
