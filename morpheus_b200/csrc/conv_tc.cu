@@ -316,7 +316,9 @@ extern "C" int mb_rows_split(const float* x, uint64_t n_elems, const float* scal
     using namespace mb;
     if (!x || !hi || !lo || (n_elems & 1)) { set_error("rows_split: bad argument (even element count)"); return MB_EINVAL; }
     if (n_elems == 0) return MB_OK;
-    const unsigned blocks = (unsigned)min<uint64_t>((n_elems / 2 + 255) / 256, 148 * 16);
+    uint64_t nb = (n_elems / 2 + 255) / 256;
+    if (nb > 148 * 16) nb = 148 * 16;
+    const unsigned blocks = (unsigned)nb;
     conv::rows_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (size_t)n_elems, scale_dev, (__half*)hi, (__half*)lo);
     return check_launch("rows_split");
 }
