@@ -415,14 +415,14 @@ def virtual_view_step(renderer, guidance, opt, view, embeddings, tr, shading='la
     opt.set_active(real_view=False, shading=shading)
     opt.zero_grad()
     H, W = view['H'], view['W']
-    rays = {k: view[k].reshape(H * W, -1) for k in ('rays_o', 'rays_d', 'rays_t', 'rays_id')}
+    rays = {k: view[k].reshape(1, H * W, -1) for k in ('rays_o', 'rays_d', 'rays_t', 'rays_id')}
     rank = 0
     if world_size > 1:
         rank = dist.get_rank()
         n = (H * W) // world_size
         if n * world_size != H * W:
             raise RuntimeError(f'virtual_view_step: {H}x{W} rays do not split evenly over {world_size} ranks')
-        rays = {k: v[rank * n:(rank + 1) * n] for k, v in rays.items()}
+        rays = {k: v[:, rank * n:(rank + 1) * n] for k, v in rays.items()}
         if t is None:       # the replicated SDS chain must draw the SAME timestep / noise on every rank
             g = torch.Generator(device=rays['rays_o'].device).manual_seed(int(opt.t) + 12345)
             t = torch.randint(guidance.min_step, guidance.max_step + 1, (1,), dtype=torch.long, device=rays['rays_o'].device, generator=g)
