@@ -152,7 +152,7 @@ def run_reference(args, rank):
     line = {'impl': 'reference', 'metric': 'rays_per_sec_train_step', 'value': val, 'unit': 'rays/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': dict(workload_config(args.config, args.gpus), sample_rays_per_step=n_rays),
+            'config': workload_config(args.config, args.gpus), 'run': {'sample_rays_per_step': n_rays},
             'extrapolated_ms_per_full_step': sec * 1e3 * (N_RAYS / n_rays),
             'cpu_baseline': {'value': val, 'unit': 'rays/s', 'cores': cores, 'kind': 'port',
                              'sample': f'{n_rays} rays x {N_SAMPLES} samples per step (1/{N_RAYS // n_rays} of the workload), fwd+bwd+Adam, torch CPU oracle port; '
@@ -449,8 +449,8 @@ def run_real_view(args, rank, world, local_rank, dev):
             ref_gpu['ours_over_reference_gpu'] = value / ref_gpu['value']
     line = {'metric': 'rays_per_sec_train_step', 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': dict(workload_config(args.config, world), cuda_graph=(not args.no_graph), full_step=bool(args.full_step),
-                           nccl_in_graph=nccl_flag),
+            'config': workload_config(args.config, world),
+            'run': {'cuda_graph': (not args.no_graph), 'full_step': bool(args.full_step), 'nccl_in_graph': nccl_flag},
             'clocks': clocks,
             'e2e': {'value': e2e_val, 'unit': 'rays/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': (launches * args.steps if launches else launches), 'gpu_launches_per_step': launches, 'kernels': kern, 'final_loss': last_loss,
@@ -538,7 +538,7 @@ def run_virtual_configs(args, rank, world, dev):
     sds_flops = 352.7e9 + 272.7e9 * 2          # UNet forward (batch 2) + VAE encoder forward + input-gradient backward
     line = {'metric': 'rays_per_sec_train_step', 'value': rays / (ms_step * 1e-3), 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': dict(workload_config(args.config, world), sds_precision=args.sds_precision, sds_chain_cuda_graph=True, max_level=0.75),
+            'config': workload_config(args.config, world), 'run': {'sds_precision': args.sds_precision, 'sds_chain_cuda_graph': True, 'max_level': 0.75},
             'clocks': clocks, 'final_loss': float(last),
             'e2e': {'value': rays / (ms_step * 1e-3), 'unit': 'rays/s', 'h2d_bytes_per_step': (10 * n_local * 68 if args.config == 'cfg5' else 0), 'd2h_bytes_per_step': 0,
                     'note': 'rays are generated on the device (virtual views) / copied from host batches inside the timed step (real views of cfg5)'},
