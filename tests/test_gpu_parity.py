@@ -963,3 +963,104 @@ def test_occupancy_refresh_vs_oracle(dev):
     assert torch.equal(est128.occs, occs1) and torch.equal(est128.binaries, bin1)
     R128.update_occ_grid(rays_t.to(dev), step=17)        # not a multiple of 16: no refresh
     assert torch.equal(est128.occs, occs1)
+
+
+# ------------------------------------------------------------------------------------------------
+# ray generation on the device, eval render, virtual-view render with the orientation loss
+# ------------------------------------------------------------------------------------------------
+def test_ray_generation_on_device_vs_reference_goldens(dev, golden_dir):
+    """SURVEY 8a-1 / 8f-3 on the GPU: the device-resident dataset (rays of the selected pixels computed on the fly, no host gather, no
+    H2D copy) and the novel-view ray generator against the goldens produced by the unmodified reference dataset methods
+    (datasets/dataset.py:336-433, :435-578; tests/golden/make_loss_golden.py)."""
+    from morpheus_b200 import rays
+    z = np.load(os.path.join(golden_dir, 'real_view_rays.npz'))
+    data = rays.RealViewData(z['images'], z['depths'], z['masks'], z['poses'], z['K'], device=dev)
+    s = data.sample_real_view_rays(idx=torch.from_numpy(z['idx']), ray_num=13, index=torch.from_numpy(z['index']))
+    assert all(s[k].is_cuda for k in ('rays_o', 'rays_d', 'rays_t', 'rays_id', 'image', 'depth', 'mask'))
+    for k in ('rays_o', 'rays_d', 'rays_t', 'image', 'depth'):
+        assert s[k].shape == z['s_' + k].shape and np.allclose(cpu(s[k]), z['s_' + k], rtol=0, atol=1e-6), k
+    for k in ('rays_id', 'mask'):
+        assert np.array_equal(cpu(s[k]), z['s_' + k]), k
+    f = data.sample_real_view_rays(idx=2)
+    for k in ('rays_o', 'rays_d', 'rays_t', 'image', 'depth'):
+        assert np.allclose(cpu(f[k]), z['f_' + k], rtol=0, atol=1e-6), k
+    v = np.load(os.path.join(golden_dir, 'virtual_views.npz'))
+    for i in range(int(v['n'])):
+        g = lambda k: v[f'v{i}_{k}']      # noqa: E731
+        w = rays.virtual_view_rays(frame=12, num_frames=200, H=360, W=360, focal=517.0, scale=0.2, theta_deg=float(g('polar')[0]) + 90.0,
+                                   phi_deg=float(g('azimuth')[0]), device=dev)
+        assert w['rays_o'].is_cuda and np.allclose(cpu(w['rays_o']), g('rays_o'), rtol=0, atol=2e-5)
+        assert np.allclose(cpu(w['rays_d']), g('rays_d'), rtol=0, atol=2e-5)
+        assert np.allclose(cpu(w['rays_t']), g('rays_t')) and np.array_equal(cpu(w['rays_id']), g('rays_id'))
+
+
+def test_eval_render_image_vs_oracle(dev):
+    """`Renderer.render_image` (eval_step, morpheus.py:1238-1269: model.eval(), chunked rays, shading 'albedo') against the
+    oracle render on the same samples -- image and depth within the north star's 1e-4."""
+    from morpheus_b200.nerfacc_compat import OccGridEstimator
+    from morpheus_b200.render import Renderer
+    from oracle import render as orr
+    from oracle.fields import SceneOracle, init_reference_like_state
+    sd = init_reference_like_state(200, seed=3, randomize=True, emb_scale=0.05, sphere=True)
+    sd['sdf2density.beta'] = torch.tensor(0.3)
+    N, S = 300, 32
+    o, d, g = _rays(N, 11)
+    aabb = torch.tensor([-1.01, -1.01, -1.01, 1.01, 1.01, 1.01])
+    jitter = torch.rand(N, generator=g)
+    t = torch.full((N, 1), 0.25)
+    ids = torch.full((N, 1), 50, dtype=torch.long)
+    sc = SceneOracle(sd, 1.01, 200, 1.0)
+    with torch.no_grad():
+        ref = orr.render_rays(sc, o, d, t, ids, orr.sample_uniform(o, d, aabb, S, jitter), bg_color=None, shading='albedo')
+    m = make_model(sd, 1.0, dev).train()
+    cfg = {'model': {'bg_radius': 1.4, 'activation': 'exp'}, 'render': {'step_size': 0.01}, 'train': {}}
+    R = Renderer(m, OccGridEstimator(aabb, 128).to(dev), cfg, 200, uniform_samples=S)
+    out = R.render_image(o.to(dev), d.to(dev), t.to(dev), ids.to(dev), chunk=512, jitter=jitter.to(dev), shading='albedo')
+    assert m.training is True                      # the previous mode is restored
+    assert rel_l2(cpu(out['image']), cpu(ref['image'])) < 1e-4 and rel_l2(cpu(out['depth']), cpu(ref['depth'])) < 1e-4
+    assert rel_l2(cpu(out['weights_sum']).reshape(-1), cpu(ref['weights_sum']).reshape(-1)) < 1e-4
+
+
+def test_virtual_view_render_with_orientation_loss_vs_oracle(dev):
+    """MorpheuS.render_rays on a VIRTUAL view (morpheus.py:558-794 with real_view=False): lambertian shading (the colour depends on the FD
+    normal and the injected light direction), white background, loss_orient = sum w.detach() max(n . d, 0)^2 (:709-712), loss_normal_perturb --
+    values and the gradients of image.sum() + loss_orient + loss_normal_perturb against the oracle's autograd.  (General path: forward FD
+    chains + field_bwd_fd_tc; the fused FD regulariser only serves real views.)"""
+    from morpheus_b200.nerfacc_compat import OccGridEstimator
+    from morpheus_b200.render import Renderer
+    from oracle import render as orr
+    from oracle.fields import SceneOracle, init_reference_like_state, safe_normalize
+    sd = init_reference_like_state(200, seed=9, randomize=True, emb_scale=0.05, sphere=True)
+    sd['sdf2density.beta'] = torch.tensor(0.3)
+    N, S = 96, 32
+    o, d, g = _rays(N, 5)
+    aabb = torch.tensor([-1.01, -1.01, -1.01, 1.01, 1.01, 1.01])
+    jitter = torch.rand(N, generator=g)
+    samples = orr.sample_uniform(o, d, aabb, S, jitter)
+    t = torch.full((N, 1), 0.4)
+    ids = torch.full((N, 1), 80, dtype=torch.long)
+    light = safe_normalize(o + torch.randn(3, generator=g))
+    noise = torch.randn(N * S, 3, generator=g)
+    sdo = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    sc = SceneOracle(sdo, 1.01, 200, 0.9)
+    ref = orr.render_rays(sc, o, d, t, ids, samples, bg_color=None, ambient_ratio=0.4, light_d=light, shading='lambertian', perturb_noise=noise,
+                          training=True, real_view=False)
+    lo = ref['image'].sum() + 0.01 * ref['loss_orient'] + ref['loss_normal_perturb']
+    lo.backward()
+    m = make_model(sd, 0.9, dev).train()
+    tr = {'ori_weight': 0.01, 'normal_smooth_3d': 0.1, 'smoothness_std': 0.005, 'topo_none': True, 'normal_dir': False, 'code_reg': 0.0, 'trunc': 0.1}
+    cfg = {'model': {'bg_radius': 1.4, 'activation': 'exp'}, 'render': {'step_size': 0.01}, 'train': tr}
+    R = Renderer(m, OccGridEstimator(aabb, 128).to(dev), cfg, 200)
+    out = R.render_rays(o.to(dev), d.to(dev), t.to(dev), ids.to(dev), bg_color=None, ambient_ratio=0.4, light_d=light.to(dev), shading='lambertian',
+                        real_view=False, samples=tuple(s.to(dev) for s in samples), perturb_noise=noise.to(dev))
+    l = out['image'].sum() + 0.01 * out['loss_orient'] + out['loss_normal_perturb']
+    l.backward()
+    assert rel_l2(cpu(out['image']).reshape(-1, 3), cpu(ref['image'])) < 1e-4
+    assert abs(float(out['loss_orient']) - float(ref['loss_orient'])) <= 2e-3 * abs(float(ref['loss_orient'])) + 1e-7
+    assert abs(float(out['loss_normal_perturb']) - float(ref['loss_normal_perturb'])) <= 2e-4 * abs(float(ref['loss_normal_perturb']))
+    errs = {}
+    for name, p in m.named_parameters():
+        if name in sdo and sdo[name].grad is not None and p.grad is not None and float(sdo[name].grad.abs().max()) > 0:
+            errs[name] = rel_l2(cpu(p.grad), cpu(sdo[name].grad))
+    bad = {k: e for k, e in errs.items() if e > 1e-2}
+    assert len(errs) >= 20 and not bad, f'{bad}\nall: {errs}'
