@@ -12,7 +12,8 @@
 //     UMMA core matrix, so the im2col gather is a cp.async of 16-byte chunks with zero-fill at the image border -- no im2col buffer;
 //   * weights are packed ONCE (frozen) per (n-tile, tap, 64-channel block) into the UMMA canonical K-major byte order (hi | lo), so a
 //     pipeline stage is one contiguous cp.async.bulk of 256 * N_TILE bytes;
-//   * tile = 128 pixels x N_TILE (128 or 160) output channels, K stage = 64 channels of one tap (4 K=16 steps), 3-stage ring;
+//   * tile = 128 pixels x N_TILE (128 or 160) output channels, K stage = 64 channels of one tap (4 K=16 steps), 3-stage ring (MB_CONV_KC /
+//     NSTG / LAG; measured alternatives on the SDS chain: 32 channels x 6 stages x lag 4 -> 19.05 ms, 64 x 3 x lag 2 -> 18.99 ms, this shape 18.4 ms);
 //     warps 0-3 gather A and later run the epilogue (TMEM -> + bias -> coalesced NCHW stores, 32 consecutive pixels per store),
 //     warp 4 streams B, warp 5 issues the MMAs; split-K over the (tap, channel-block) stages (gridDim.z) with red.global.add fills
 //     the machine for the small-M layers of the UNet (M = 2 x 32 x 32 ... 2 x 4 x 4).
@@ -24,18 +25,30 @@ namespace conv {
 using namespace mb::tc;
 
 constexpr int TM = 128;             // pixels per tile
-constexpr int KC = 64;              // channels per pipeline stage (one tap)
-constexpr int NSTG = 3;
+#ifndef MB_CONV_KC
+#define MB_CONV_KC 64
+#endif
+#ifndef MB_CONV_NSTG
+#define MB_CONV_NSTG 3
+#endif
+#ifndef MB_CONV_LAG
+#define MB_CONV_LAG 1
+#endif
+constexpr int KC = MB_CONV_KC;      // channels per pipeline stage (one tap); weights are packed in 64-channel blocks = 64 / KC stages
+constexpr int KB = 64;              // channel block of the weight pack / of the host-side divisibility rule
+constexpr int NSTG = MB_CONV_NSTG;  // ring depth
+constexpr int LAG = MB_CONV_LAG;    // a producer publishes stage i - LAG after issuing stage i (LAG + 1 cp.async groups in flight per thread)
+static_assert(LAG >= 1 && LAG < NSTG && KB % KC == 0 && KC % 16 == 0, "pipeline shape");
 constexpr int A_STAGE = 2 * (KC / 8) * TM * 16;      // hi + lo: 8 K-cores x 128 rows x 16 B each = 32768
 constexpr int A_LO = A_STAGE / 2;
 constexpr int NTHREADS = 192;       // 4 producer / epilogue warps + B loader warp + MMA warp
 
 template <int N_TILE>
 struct Smem {
-    static constexpr int B_STAGE = 256 * N_TILE;                       // 4 slabs x (hi + lo) x 2 K-cores x N_TILE rows x 16 B
+    static constexpr int B_STAGE = (KC / 16) * 64 * N_TILE;            // KC / 16 slabs x (hi + lo) x 2 K-cores x N_TILE rows x 16 B
     static constexpr int A = 0;
     static constexpr int B = NSTG * A_STAGE;
-    static constexpr int BAR = B + NSTG * B_STAGE;                     // full_a[3], full_b[3], empty[3], acc_ready
+    static constexpr int BAR = B + NSTG * B_STAGE;                     // full_a[NSTG], full_b[NSTG], empty[NSTG], acc_ready
     static constexpr int TMEMH = BAR + 8 * (3 * NSTG + 1);
     static constexpr int TOTAL = TMEMH + 16;
 };
@@ -113,16 +126,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_kernel(const Args a) {
                 cp_async16_zfill(dst + A_LO + kc * (TM * 16), sl + kc * 8, nb);
             }
             cp_async_commit();
-            if (i >= 1) {                                // stage i-1 has landed: publish it to the tensor core (async proxy)
-                cp_async_wait<1>();
+            if (i >= LAG) {                              // stage i-LAG has landed: publish it to the tensor core (async proxy)
+                cp_async_wait<LAG>();
                 fence_proxy_async();
-                mbar_arrive(full_a + (i - 1) % NSTG);
+                mbar_arrive(full_a + (i - LAG) % NSTG);
             }
         }
-        if (n_st > 0) {
+        {   // drain: the last min(LAG, n_st) stages
             cp_async_wait<0>();
             fence_proxy_async();
-            mbar_arrive(full_a + (n_st - 1) % NSTG);
+            for (int i = (n_st > LAG ? n_st - LAG : 0); i < n_st; i++) mbar_arrive(full_a + i % NSTG);
         }
         // ======================= epilogue: TMEM -> (+ bias) -> NCHW fp32, 32 consecutive pixels per store instruction =======================
         mbar_wait(acc_ready, 0);
@@ -211,7 +224,7 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int Cout_w, int Ci
     const int K = transposed ? Cout_w : Cin_w;        // channels contracted per tap
     const int cblocks = K / KC, n_tiles = N / n_tile;
     const size_t total = (size_t)N * K * ntaps;
-    const size_t stage_bytes = (size_t)256 * n_tile;
+    const size_t stage_bytes = (size_t)(KC / 16) * 64 * n_tile;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % K);
         const int tap = (int)((i / K) % ntaps);
