@@ -29,6 +29,7 @@ _TC_TABLES = {}
 
 _TC_TABLES_T = {}
 _TC_TABLES_S = {}
+_TC_TABLES_ALL = {}
 
 
 def _tc_tables_small(dev):
@@ -490,11 +491,12 @@ class _FDRegulariser(torch.autograd.Function):
         P.n_levels, P.n_freq = n_levels, n_freq
         normal = torch.empty(M, 3, device=dev, dtype=torch.float32)
         normal_raw = torch.empty(M, 3, device=dev, dtype=torch.float32)
-        loss = torch.zeros(1, device=dev, dtype=torch.float32)
+        # one zero-fill launch for the three accumulation targets (loss | table gradient | arena gradient)
+        n_e, n_a = emb_sdf.numel(), arena.numel()
+        acc = torch.zeros(4 + n_e + n_a, device=dev, dtype=torch.float32)
+        loss, g_emb, g_arena = acc[:1], acc[4:4 + n_e].view(emb_sdf.shape), acc[4 + n_e:].view(arena.shape)
         g_x = torch.empty(M, 3, device=dev, dtype=torch.float32)
         g_topo = torch.empty(M, 2, device=dev, dtype=torch.float32) if topo is not None else None
-        g_emb = torch.zeros_like(emb_sdf)
-        g_arena = torch.zeros_like(arena)
         tabs_f, tabs_s = _tc_tables(dev), _tc_tables_small(dev)
         with _lib.timed('fd_regulariser'):
             check(_lib.lib().mb_fd_regulariser_tc(_lib.C.byref(P), ptr(x), ptr(topo_c), ptr(noise_c), _lib.C.c_float(noise_std), M, _lib.C.c_float(gmul),
@@ -504,7 +506,7 @@ class _FDRegulariser(torch.autograd.Function):
         ctx.has_topo = topo is not None
         ctx.save_for_backward(g_x, g_topo, g_emb, g_arena)
         ctx.mark_non_differentiable(normal, normal_raw)
-        return loss[0], normal, normal_raw
+        return loss[0].clone(), normal, normal_raw
 
     @staticmethod
     def backward(ctx, g_loss, _gn, _gr):
@@ -515,7 +517,8 @@ class _FDRegulariser(torch.autograd.Function):
             g_emb_out = None
         else:
             g_emb_out = g_emb * g
-        return None, g_x * g, (g_topo * g if ctx.has_topo else None), None, g_arena * g, g_emb_out
+        outs = torch._foreach_mul([g_x, g_topo, g_arena] if ctx.has_topo else [g_x, g_arena], g)      # one launch for the per-sample / arena scalings
+        return None, outs[0], (outs[1] if ctx.has_topo else None), None, outs[-1], g_emb_out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -639,15 +642,25 @@ class scene_representation(nn.Module):
     @staticmethod
     def _pack_tc(arena):
         """fp16 (hi, lo) tensor-core operand slabs of the arena: forward table, dgrad table of the deform/topology nets,
-        dgrad table of the SDF/colour nets (mb_pack_tc); shared by every query and backward until the arena changes"""
+        dgrad table of the SDF/colour nets -- packed by ONE mb_pack_tc launch into one buffer (the three tables are views);
+        shared by every query and backward until the arena changes"""
         dev = arena.device
-        out = {}
-        for name, (tabs, n) in (('f', (_tc_tables(dev), 18)), ('t', (_tc_tables_dgrad(dev), 12)), ('s', (_tc_tables_small(dev), 6))):
-            w = torch.empty(tabs[2], dtype=torch.uint8, device=dev)
-            with _lib.timed('pack_tc'):
-                check(_lib.lib().mb_pack_tc(ptr(arena), ptr(tabs[0]), n, ptr(w), stream()), 'pack_tc')
-            out[name] = w
-        return out
+        key = str(dev)
+        if key not in _TC_TABLES_ALL:
+            parts = [('f', _tc_tables(dev)), ('t', _tc_tables_dgrad(dev)), ('s', _tc_tables_small(dev))]
+            descs, spans, base = [], {}, 0
+            for name, tabs in parts:
+                d = tabs[0].clone()
+                d[:, 5] += base                      # dst_off of every layer, relative to the combined buffer
+                descs.append(d)
+                spans[name] = (base, base + int(tabs[2]))
+                base += (int(tabs[2]) + 1023) // 1024 * 1024
+            _TC_TABLES_ALL[key] = (torch.cat(descs, 0).contiguous(), spans, base)
+        desc, spans, total = _TC_TABLES_ALL[key]
+        w = torch.empty(total, dtype=torch.uint8, device=dev)
+        with _lib.timed('pack_tc'):
+            check(_lib.lib().mb_pack_tc(ptr(arena), ptr(desc), int(desc.shape[0]), ptr(w), stream()), 'pack_tc')
+        return {name: w[a:b] for name, (a, b) in spans.items()}
 
     def invalidate(self):
         self._arena_cache = None
