@@ -394,10 +394,10 @@ class _AllGatherRows(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, world, rank):
         x = x.contiguous()
-        out = torch.empty((world,) + tuple(x.shape), device=x.device, dtype=x.dtype)
+        out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)      # concatenated form: NCCL and gloo
         dist.all_gather_into_tensor(out, x)
         ctx.rank, ctx.n = rank, x.shape[0]
-        return out.reshape((world * x.shape[0],) + tuple(x.shape[1:]))
+        return out
 
     @staticmethod
     def backward(ctx, g):

@@ -80,3 +80,63 @@ def test_sharded_gradient_equals_single_process(shipped):
         p.join(60)
         assert p.exitcode == 0
     torch.testing.assert_close(got, th.grad, rtol=1e-5, atol=1e-6)
+
+
+# ---- round 2: the other sharding rules of the step (masked means with global counts, sum-type terms, all-gathered image) ----
+def _problem2():
+    g = torch.Generator().manual_seed(1)
+    N = 8
+    theta = torch.randn(4, generator=g)
+    feats = torch.randn(N, 4, generator=g)
+    valid = torch.tensor([1.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, 1.0])           # uneven number of valid points per shard
+    target = torch.rand(N, 3, generator=g)
+    return N, theta, feats, valid, target
+
+
+def _loss2(theta, lo, hi, world, rank, N, feats, valid, target):
+    """a shard's loss: masked mean over valid points (denominator = GLOBAL count), a SUM-type term (loss_orient, morpheus.py:712), and a
+    replicated loss on the all-gathered per-ray image (the SDS chain of a ray-sharded novel view)"""
+    from morpheus_b200.render import global_count
+    from morpheus_b200.train import _AllGatherRows, weighted_sum
+    y = feats[lo:hi] @ theta                                                   # per-ray quantity of this shard
+    n_valid = global_count(valid[lo:hi].sum(), world) if world > 1 else valid[lo:hi].sum()
+    masked_mean = (y.square() * valid[lo:hi]).sum() / n_valid.clamp(min=1.0)
+    sum_term = torch.relu(y).square().sum() * world                            # world x local sum: (loss / world) summed over ranks = global sum
+    img = torch.sigmoid(y)[:, None] * torch.ones(1, 3)
+    if world > 1:
+        img = _AllGatherRows.apply(img, world, rank)
+    replicated = (img - target).square().sum()                                 # identical on every rank; its gradient reaches each shard unscaled
+    return weighted_sum([masked_mean, sum_term], [10.0 / world, 0.01 / world]) + replicated
+
+
+def _worker2(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    N, theta, *rest = _problem2()
+    th = theta.clone().requires_grad_(True)
+    n_local = N // world
+    _loss2(th, rank * n_local, (rank + 1) * n_local, world, rank, N, *rest).backward()
+    flat = th.grad.clone()
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        q.put(flat)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_round2_sharding_rules_equal_single_process():
+    N, theta, *rest = _problem2()
+    th = theta.clone().requires_grad_(True)
+    _loss2(th, 0, N, 1, 0, N, *rest).backward()
+    ctx = mp.get_context('spawn')
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker2, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    torch.testing.assert_close(got, th.grad, rtol=1e-5, atol=1e-6)
